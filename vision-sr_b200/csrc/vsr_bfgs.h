@@ -1,0 +1,764 @@
+// vsr_bfgs.h -- one BFGS run as a resumable state machine.
+//
+// Restates what the reference gets from
+//     scipy.optimize.minimize(safe_loss, x0, method='BFGS')
+// (reference src/visymre/architectures/bfgs.py:115 and :179; scipy is an unpinned
+// dependency of the reference, the algorithm below follows scipy 1.18.1):
+//   _minimize_bfgs              scipy/optimize/_optimize.py:1345-1530
+//   _line_search_wolfe12        scipy/optimize/_optimize.py:1156-1199
+//   line_search_wolfe1 / scalar_search_wolfe1   scipy/optimize/_linesearch.py:37-190
+//   DCSRCH / dcstep (MINPACK-2) scipy/optimize/_dcsrch.py
+//   line_search_wolfe2 / scalar_search_wolfe2 / _zoom / _cubicmin / _quadmin
+//                               scipy/optimize/_linesearch.py:192-680
+//   ScalarFunction caching      scipy/optimize/_differentiable_functions.py:128-420
+//   '2-point' forward difference scipy/optimize/_numdiff.py:580-700
+//
+// Why a state machine: on the GPU one CTA owns one (candidate, restart) run.  Thread 0
+// advances the optimiser until it needs the objective at a new point, then returns
+// VSR_NEED_EVAL; ALL threads of the CTA then sweep the data points together (they
+// reach the sweep convergently, so warp shuffles and __syncthreads are legal), and
+// thread 0 resumes.  scipy's nested calls (BFGS -> line search -> phi/derphi ->
+// ScalarFunction) are flattened into one protothread-style function; every variable
+// that lives across an evaluation is a member of FitState.
+//
+// The same header is compiled by g++ into oracle/hostsim (CPU tests check the logic
+// against scipy itself); the product path only runs the CUDA build.
+#ifndef VSR_BFGS_H_
+#define VSR_BFGS_H_
+
+#include "vsr_isa.h"
+
+#if defined(__CUDACC__)
+#define VSR_HDN __host__ __device__
+#else
+#include <cmath>
+#define VSR_HDN
+#endif
+
+namespace vsr {
+
+struct FitOpts {
+  double gtol;        // 1e-5   (_optimize.py:1346)
+  double c1;          // 1e-4
+  double c2;          // 0.9
+  double xrtol;       // 0
+  double fd_eps;      // sqrt(eps) = 1.4901161193847656e-08 (_optimize.py:192)
+  double penalty;     // 1e6    (bfgs.py:109)
+  double loss_scale;  // 1 (MSE) or 1/mean(y) (NMSE, bfgs.py:85-90)
+  double stop_time;   // seconds; the loss turns into `penalty` afterwards (bfgs.py:23-36)
+  int maxiter_per_k;  // 200    (_optimize.py:1414)
+  int grad_mode;      // VsrGradMode
+};
+
+enum { VSR_NEED_EVAL = 1, VSR_DONE = 0 };
+
+// DCSRCH task codes
+enum { DC_START = 0, DC_FG = 1, DC_CONV = 2, DC_WARN = 3, DC_ERROR = 4 };
+
+struct FitState {
+  int pc;  // resume label of the protothread
+  int k;   // number of constants
+  // ---- request / response of one sweep over the points ----
+  double* xe;  // [k] point the sweep must evaluate
+  double rf;   // objective there (scaled, penalty applied)
+  double* rg;  // [k] its gradient (dual mode only)
+  // ---- ScalarFunction cache ----
+  double* cx;  // [k] current point of the cache
+  double* cg;  // [k] gradient at cx
+  double cf;
+  int f_ok, g_ok;
+  int nfev, ngev;
+  int fd_i;
+  double fd_dx;
+  double* lastx;  // [k] last point the objective was evaluated at (TimedFun.x, bfgs.py:35)
+  // ---- BFGS ----
+  double* xk;    // [k]
+  double* gfk;   // [k]
+  double* pk;    // [k]
+  double* xt;    // [k] trial point xk + a*pk
+  double* gnew;  // [k] gradient returned by the line search
+  double* H;     // [k*k] inverse Hessian estimate
+  double* Hy;    // [k] scratch
+  int it, maxiter, warnflag, status;
+  double old_fval, old_old_fval, gnorm, alpha_k;
+  int have_gnew;
+  // ---- line search (shared by wolfe1 and wolfe2) ----
+  double phi0, derphi0, old_phi0;
+  double stp, phi1, derphi1;
+  int task, ls_i, ls_ok;
+  double ls_fval, ls_oldfval;
+  // DCSRCH state (_dcsrch.py)
+  int brackt, stage;
+  double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1;
+  // wolfe2 / zoom
+  double alpha0, alpha1, phi_a0, phi_a1, derphi_a0, derphi_a1;
+  double a_lo, a_hi, phi_lo, phi_hi, derphi_lo, a_rec, phi_rec, a_j, phi_aj, derphi_aj;
+  int zi, w2_i, zoom_ok, star_has_der;
+  double alpha_star, phi_star;
+};
+
+// number of doubles of workspace fit_init() carves for a run with k constants
+VSR_HDN inline int fit_workspace_doubles(int k) { return 11 * k + k * k; }
+
+VSR_HDN inline void fit_init(FitState& S, int k, double* ws, const double* x0) {
+  S.k = k;
+  S.xe = ws;
+  S.rg = ws + k;
+  S.cx = ws + 2 * k;
+  S.cg = ws + 3 * k;
+  S.lastx = ws + 4 * k;
+  S.xk = ws + 5 * k;
+  S.gfk = ws + 6 * k;
+  S.pk = ws + 7 * k;
+  S.xt = ws + 8 * k;
+  S.gnew = ws + 9 * k;
+  S.Hy = ws + 10 * k;
+  S.H = ws + 11 * k;
+  for (int i = 0; i < k; ++i) {
+    S.xk[i] = x0[i];
+    S.lastx[i] = x0[i];
+  }
+  S.pc = 0;
+  S.f_ok = S.g_ok = 0;
+  S.nfev = S.ngev = 0;
+  S.it = 0;
+  S.warnflag = 0;
+  S.status = 0;
+  S.rf = 0.0;
+}
+
+namespace detail {
+
+VSR_HDN inline bool finite_d(double x) {
+#if defined(__CUDA_ARCH__)
+  return isfinite(x);
+#else
+  return std::isfinite(x);
+#endif
+}
+VSR_HDN inline bool nan_d(double x) { return x != x; }
+VSR_HDN inline double abs_d(double x) { return ::fabs(x); }
+VSR_HDN inline double max_d(double a, double b) { return b > a ? b : a; }  // python max(a, b): a unless b > a
+VSR_HDN inline double min_d(double a, double b) { return b < a ? b : a; }  // python min(a, b)
+VSR_HDN inline double clip_d(double x, double lo, double hi) {
+  // np.clip = minimum(maximum(x, lo), hi), nan propagates
+  if (nan_d(x)) return x;
+  double t = x < lo ? lo : x;
+  return t > hi ? hi : t;
+}
+VSR_HDN inline double sign_d(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : (x == 0 ? 0.0 : x)); }
+
+// dcstep (_dcsrch.py:502-728): safeguarded cubic/quadratic step of More-Thuente.
+VSR_HDN inline void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy,
+                           double& dy, double& stp, double fp, double dp, int& brackt,
+                           double stpmin, double stpmax) {
+  const double sgnd = sign_d(dp) * sign_d(dx);
+  double stpf, stpc, stpq, theta, s, gamma, p, q, r;
+  if (fp > fx) {
+    theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+    s = max_d(max_d(abs_d(theta), abs_d(dx)), abs_d(dp));
+    gamma = s * ::sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+    if (stp < stx) gamma = -gamma;
+    p = (gamma - dx) + theta;
+    q = ((gamma - dx) + gamma) + dp;
+    r = p / q;
+    stpc = stx + r * (stp - stx);
+    stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
+    if (abs_d(stpc - stx) <= abs_d(stpq - stx))
+      stpf = stpc;
+    else
+      stpf = stpc + (stpq - stpc) / 2.0;
+    brackt = 1;
+  } else if (sgnd < 0.0) {
+    theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+    s = max_d(max_d(abs_d(theta), abs_d(dx)), abs_d(dp));
+    gamma = s * ::sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+    if (stp > stx) gamma = -gamma;
+    p = (gamma - dp) + theta;
+    q = ((gamma - dp) + gamma) + dx;
+    r = p / q;
+    stpc = stp + r * (stx - stp);
+    stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    if (abs_d(stpc - stp) > abs_d(stpq - stp))
+      stpf = stpc;
+    else
+      stpf = stpq;
+    brackt = 1;
+  } else if (abs_d(dp) < abs_d(dx)) {
+    theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+    s = max_d(max_d(abs_d(theta), abs_d(dx)), abs_d(dp));
+    double rad = (theta / s) * (theta / s) - (dx / s) * (dp / s);
+    rad = max_d(0.0, rad);  // python max(0, nan) == 0
+    gamma = s * ::sqrt(rad);
+    if (stp > stx) gamma = -gamma;
+    p = (gamma - dp) + theta;
+    q = (gamma + (dx - dp)) + gamma;
+    r = p / q;
+    if (r < 0 && gamma != 0)
+      stpc = stp + r * (stx - stp);
+    else if (stp > stx)
+      stpc = stpmax;
+    else
+      stpc = stpmin;
+    stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    if (brackt) {
+      if (abs_d(stpc - stp) < abs_d(stpq - stp))
+        stpf = stpc;
+      else
+        stpf = stpq;
+      if (stp > stx)
+        stpf = min_d(stp + 0.66 * (sty - stp), stpf);
+      else
+        stpf = max_d(stp + 0.66 * (sty - stp), stpf);
+    } else {
+      if (abs_d(stpc - stp) > abs_d(stpq - stp))
+        stpf = stpc;
+      else
+        stpf = stpq;
+      stpf = clip_d(stpf, stpmin, stpmax);
+    }
+  } else {
+    if (brackt) {
+      theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
+      s = max_d(max_d(abs_d(theta), abs_d(dy)), abs_d(dp));
+      gamma = s * ::sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
+      if (stp > sty) gamma = -gamma;
+      p = (gamma - dp) + theta;
+      q = ((gamma - dp) + gamma) + dy;
+      r = p / q;
+      stpc = stp + r * (sty - stp);
+      stpf = stpc;
+    } else if (stp > stx) {
+      stpf = stpmax;
+    } else {
+      stpf = stpmin;
+    }
+  }
+  if (fp > fx) {
+    sty = stp;
+    fy = fp;
+    dy = dp;
+  } else {
+    if (sgnd < 0) {
+      sty = stx;
+      fy = fx;
+      dy = dx;
+    }
+    stx = stp;
+    fx = fp;
+    dx = dp;
+  }
+  stp = stpf;
+}
+
+// DCSRCH._iterate (_dcsrch.py:244-500).  ftol = c1, gtol = c2.
+VSR_HDN inline void dcsrch_iterate(FitState& S, double& stp, double f, double g, int& task,
+                                   double ftol, double gtol, double xtol, double stpmin,
+                                   double stpmax) {
+  const double p5 = 0.5, p66 = 0.66, xtrapl = 1.1, xtrapu = 4.0;
+  if (task == DC_START) {
+    if (stp < stpmin) task = DC_ERROR;
+    if (stp > stpmax) task = DC_ERROR;
+    if (g >= 0) task = DC_ERROR;
+    if (task == DC_ERROR) return;
+    S.brackt = 0;
+    S.stage = 1;
+    S.finit = f;
+    S.ginit = g;
+    S.gtest = ftol * S.ginit;
+    S.width = stpmax - stpmin;
+    S.width1 = S.width / p5;
+    S.stx = 0.0;
+    S.fx = S.finit;
+    S.gx = S.ginit;
+    S.sty = 0.0;
+    S.fy = S.finit;
+    S.gy = S.ginit;
+    S.stmin = 0.0;
+    S.stmax = stp + xtrapu * stp;
+    task = DC_FG;
+    return;
+  }
+  const double ftest = S.finit + stp * S.gtest;
+  if (S.stage == 1 && f <= ftest && g >= 0) S.stage = 2;
+  // warnings, then convergence (a later test overrides an earlier one)
+  if (S.brackt && (stp <= S.stmin || stp >= S.stmax)) task = DC_WARN;
+  if (S.brackt && S.stmax - S.stmin <= xtol * S.stmax) task = DC_WARN;
+  if (stp == stpmax && f <= ftest && g <= S.gtest) task = DC_WARN;
+  if (stp == stpmin && (f > ftest || g >= S.gtest)) task = DC_WARN;
+  if (f <= ftest && abs_d(g) <= gtol * -S.ginit) task = DC_CONV;
+  if (task == DC_WARN || task == DC_CONV) return;
+
+  if (S.stage == 1 && f <= S.fx && f > ftest) {
+    const double fm = f - stp * S.gtest;
+    double fxm = S.fx - S.stx * S.gtest;
+    double fym = S.fy - S.sty * S.gtest;
+    const double gm = g - S.gtest;
+    double gxm = S.gx - S.gtest;
+    double gym = S.gy - S.gtest;
+    dcstep(S.stx, fxm, gxm, S.sty, fym, gym, stp, fm, gm, S.brackt, S.stmin, S.stmax);
+    S.fx = fxm + S.stx * S.gtest;
+    S.fy = fym + S.sty * S.gtest;
+    S.gx = gxm + S.gtest;
+    S.gy = gym + S.gtest;
+  } else {
+    dcstep(S.stx, S.fx, S.gx, S.sty, S.fy, S.gy, stp, f, g, S.brackt, S.stmin, S.stmax);
+  }
+  if (S.brackt) {
+    if (abs_d(S.sty - S.stx) >= p66 * S.width1) stp = S.stx + p5 * (S.sty - S.stx);
+    S.width1 = S.width;
+    S.width = abs_d(S.sty - S.stx);
+  }
+  if (S.brackt) {
+    S.stmin = min_d(S.stx, S.sty);
+    S.stmax = max_d(S.stx, S.sty);
+  } else {
+    S.stmin = stp + xtrapl * (stp - S.stx);
+    S.stmax = stp + xtrapu * (stp - S.stx);
+  }
+  stp = clip_d(stp, stpmin, stpmax);
+  if ((S.brackt && (stp <= S.stmin || stp >= S.stmax)) ||
+      (S.brackt && S.stmax - S.stmin <= xtol * S.stmax))
+    stp = S.stx;
+  task = DC_FG;
+}
+
+// _cubicmin / _quadmin (_linesearch.py): a non-finite result means "None".
+VSR_HDN inline bool cubicmin(double a, double fa, double fpa, double b, double fb, double c,
+                             double fc, double& xmin) {
+  const double C = fpa;
+  const double db = b - a, dc = c - a;
+  const double denom = (db * dc) * (db * dc) * (db - dc);
+  const double r0 = fb - fa - C * db, r1 = fc - fa - C * dc;
+  double A = (dc * dc) * r0 + (-(db * db)) * r1;
+  double B = (-(dc * dc * dc)) * r0 + (db * db * db) * r1;
+  if (denom == 0.0) return false;
+  A /= denom;
+  B /= denom;
+  const double radical = B * B - 3 * A * C;
+  if (!(radical >= 0.0) || A == 0.0) return false;
+  xmin = a + (-B + ::sqrt(radical)) / (3 * A);
+  return finite_d(xmin);
+}
+VSR_HDN inline bool quadmin(double a, double fa, double fpa, double b, double fb, double& xmin) {
+  const double D = fa, C = fpa;
+  const double db = b - a * 1.0;
+  if (db * db == 0.0) return false;
+  const double B = (fb - D - C * db) / (db * db);
+  if (B == 0.0 || !finite_d(B)) return false;
+  xmin = a - C / (2.0 * B);
+  return finite_d(xmin);
+}
+
+}  // namespace detail
+
+// ---- protothread plumbing -----------------------------------------------------------
+#define VSR_CO_YIELD_(S, n)   \
+  do {                        \
+    (S).pc = (n) + 1;         \
+    return VSR_NEED_EVAL;     \
+    case (n) + 1:;            \
+  } while (0)
+#define VSR_CO_YIELD(S) VSR_CO_YIELD_(S, __COUNTER__)
+
+// ScalarFunction._update_x via fun()/grad(): np.array_equal(x, self.x)
+#define VSR_OBJ_SETX(S, xptr)                          \
+  do {                                                 \
+    int same_ = 1;                                     \
+    for (int i_ = 0; i_ < (S).k; ++i_)                 \
+      if (!((xptr)[i_] == (S).cx[i_])) same_ = 0;      \
+    if (!same_) {                                      \
+      for (int i_ = 0; i_ < (S).k; ++i_) (S).cx[i_] = (xptr)[i_]; \
+      (S).f_ok = 0;                                    \
+      (S).g_ok = 0;                                    \
+    }                                                  \
+  } while (0)
+
+// ScalarFunction._update_fun.  In dual mode one sweep returns f and its gradient.
+#define VSR_OBJ_UPDATE_FUN(S, O)                                         \
+  do {                                                                   \
+    if (!(S).f_ok) {                                                     \
+      for (int i_ = 0; i_ < (S).k; ++i_) (S).xe[i_] = (S).cx[i_];        \
+      VSR_CO_YIELD(S);                                                   \
+      (S).cf = (S).rf;                                                   \
+      (S).nfev += 1;                                                     \
+      (S).f_ok = 1;                                                      \
+      for (int i_ = 0; i_ < (S).k; ++i_) (S).lastx[i_] = (S).xe[i_];     \
+      if ((O).grad_mode == VSR_GRAD_DUAL) {                              \
+        for (int i_ = 0; i_ < (S).k; ++i_) (S).cg[i_] = (S).rg[i_];      \
+        (S).g_ok = 1;                                                    \
+        (S).ngev += 1;                                                   \
+      }                                                                  \
+    }                                                                    \
+  } while (0)
+
+// ScalarFunction._update_grad; FD branch = approx_derivative('2-point', abs_step=eps)
+#define VSR_OBJ_UPDATE_GRAD(S, O)                                                    \
+  do {                                                                               \
+    if (!(S).g_ok) {                                                                 \
+      VSR_OBJ_UPDATE_FUN(S, O);                                                      \
+      if (!(S).g_ok) {                                                               \
+        for ((S).fd_i = 0; (S).fd_i < (S).k; ++(S).fd_i) {                           \
+          {                                                                          \
+            const double x_ = (S).cx[(S).fd_i];                                      \
+            double h_ = (O).fd_eps;                                                  \
+            if ((x_ + h_) - x_ == 0.0) {                                             \
+              const double a_ = ::fabs(x_) > 1.0 ? ::fabs(x_) : 1.0;                 \
+              h_ = 1.4901161193847656e-08 * (x_ >= 0 ? 1.0 : -1.0) * a_;             \
+            }                                                                        \
+            (S).fd_dx = (x_ + h_) - x_;                                              \
+            for (int i_ = 0; i_ < (S).k; ++i_) (S).xe[i_] = (S).cx[i_];              \
+            (S).xe[(S).fd_i] = x_ + h_;                                              \
+          }                                                                          \
+          VSR_CO_YIELD(S);                                                           \
+          (S).cg[(S).fd_i] = ((S).rf - (S).cf) / (S).fd_dx;                          \
+          (S).nfev += 1;                                                             \
+          for (int i_ = 0; i_ < (S).k; ++i_) (S).lastx[i_] = (S).xe[i_];             \
+        }                                                                            \
+        (S).g_ok = 1;                                                                \
+        (S).ngev += 1;                                                               \
+      }                                                                              \
+    }                                                                                \
+  } while (0)
+
+// phi(a) = f(xk + a*pk) ; derphi(a) = grad(xk + a*pk) . pk   (closures of
+// line_search_wolfe1/2).  The trial point is rebuilt with the same arithmetic scipy
+// uses so the ScalarFunction cache hits exactly when scipy's does.
+#define VSR_LS_PHI(S, O, a, out)                                                  \
+  do {                                                                            \
+    for (int i_ = 0; i_ < (S).k; ++i_) (S).xt[i_] = (S).xk[i_] + (a) * (S).pk[i_]; \
+    VSR_OBJ_SETX(S, (S).xt);                                                      \
+    VSR_OBJ_UPDATE_FUN(S, O);                                                     \
+    (out) = (S).cf;                                                               \
+  } while (0)
+#define VSR_LS_DERPHI(S, O, a, out)                                               \
+  do {                                                                            \
+    for (int i_ = 0; i_ < (S).k; ++i_) (S).xt[i_] = (S).xk[i_] + (a) * (S).pk[i_]; \
+    VSR_OBJ_SETX(S, (S).xt);                                                      \
+    VSR_OBJ_UPDATE_GRAD(S, O);                                                    \
+    {                                                                             \
+      double d_ = 0.0;                                                            \
+      for (int i_ = 0; i_ < (S).k; ++i_) {                                        \
+        (S).gnew[i_] = (S).cg[i_];                                                \
+        d_ += (S).cg[i_] * (S).pk[i_];                                            \
+      }                                                                           \
+      (S).have_gnew = 1;                                                          \
+      (out) = d_;                                                                 \
+    }                                                                             \
+  } while (0)
+
+// Advance the run.  Returns VSR_NEED_EVAL when the caller must evaluate the objective
+// at S.xe (store it in S.rf, and its gradient in S.rg in dual mode), VSR_DONE when
+// finished (result: S.xk, S.old_fval, S.status, S.it, S.nfev, S.lastx).
+VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
+  using namespace detail;
+  const int k = S.k;
+  switch (S.pc) {
+    case 0:
+      // ScalarFunction.__init__: f and grad at x0
+      for (int i = 0; i < k; ++i) S.cx[i] = S.xk[i];
+      S.f_ok = S.g_ok = 0;
+      VSR_OBJ_UPDATE_FUN(S, O);
+      VSR_OBJ_UPDATE_GRAD(S, O);
+      S.old_fval = S.cf;
+      for (int i = 0; i < k; ++i) S.gfk[i] = S.cg[i];
+      S.it = 0;
+      S.maxiter = k * O.maxiter_per_k;
+      for (int i = 0; i < k * k; ++i) S.H[i] = 0.0;
+      for (int i = 0; i < k; ++i) S.H[i * k + i] = 1.0;
+      {
+        double n2 = 0.0, gm = 0.0;
+        bool gnan = false;
+        for (int i = 0; i < k; ++i) {
+          n2 += S.gfk[i] * S.gfk[i];
+          if (nan_d(S.gfk[i])) gnan = true;
+          if (abs_d(S.gfk[i]) > gm) gm = abs_d(S.gfk[i]);
+        }
+        S.old_old_fval = S.old_fval + ::sqrt(n2) / 2;
+        S.gnorm = gnan ? ::nan("") : gm;  // vecnorm(gfk, inf) = amax(|gfk|), nan propagates
+      }
+      S.warnflag = 0;
+
+      while (S.gnorm > O.gtol && S.it < S.maxiter) {
+        // pk = -Hk . gfk
+        for (int i = 0; i < k; ++i) {
+          double acc = 0.0;
+          for (int j = 0; j < k; ++j) acc += S.H[i * k + j] * S.gfk[j];
+          S.pk[i] = -acc;
+        }
+        // ---------------- line_search_wolfe1 ----------------
+        {
+          double d = 0.0;
+          for (int i = 0; i < k; ++i) d += S.gfk[i] * S.pk[i];
+          S.derphi0 = d;
+        }
+        S.phi0 = S.old_fval;
+        S.old_phi0 = S.old_old_fval;
+        S.have_gnew = 0;  // gval = [gfk]
+        if (S.derphi0 != 0) {
+          S.alpha1 = min_d(1.0, 1.01 * 2 * (S.phi0 - S.old_phi0) / S.derphi0);
+          if (S.alpha1 < 0) S.alpha1 = 1.0;
+        } else {
+          S.alpha1 = 1.0;
+        }
+        S.phi1 = S.phi0;
+        S.derphi1 = S.derphi0;
+        S.task = DC_START;
+        S.ls_ok = 0;
+        S.stp = S.alpha1;
+        for (S.ls_i = 0; S.ls_i < 100; ++S.ls_i) {
+          S.stp = S.alpha1;
+          dcsrch_iterate(S, S.stp, S.phi1, S.derphi1, S.task, O.c1, O.c2, 1e-14, 1e-100, 1e100);
+          if (!finite_d(S.stp)) {
+            S.task = DC_WARN;
+            break;
+          }
+          if (S.task == DC_FG) {
+            S.alpha1 = S.stp;
+            VSR_LS_PHI(S, O, S.stp, S.phi1);
+            VSR_LS_DERPHI(S, O, S.stp, S.derphi1);
+          } else {
+            break;
+          }
+        }
+        if (S.ls_i >= 100) S.task = DC_WARN;  // for-else: did not converge
+        S.ls_ok = (S.task == DC_CONV);
+        if (S.ls_ok) {
+          S.alpha_k = S.stp;
+          S.ls_fval = S.phi1;
+          S.ls_oldfval = S.phi0;
+          // gval[0]: gradient of the last derphi call (gfk when there was none)
+          if (!S.have_gnew)
+            for (int i = 0; i < k; ++i) S.gnew[i] = S.gfk[i];
+          S.have_gnew = 1;
+        } else {
+          // ---------------- line_search_wolfe2 (fallback) ----------------
+          S.have_gnew = 0;
+          S.alpha0 = 0.0;
+          if (S.derphi0 != 0)
+            S.alpha1 = min_d(1.0, 1.01 * 2 * (S.phi0 - S.old_phi0) / S.derphi0);
+          else
+            S.alpha1 = 1.0;
+          if (S.alpha1 < 0) S.alpha1 = 1.0;
+          S.alpha1 = min_d(S.alpha1, 1e100);
+          VSR_LS_PHI(S, O, S.alpha1, S.phi_a1);
+          S.phi_a0 = S.phi0;
+          S.derphi_a0 = S.derphi0;
+          S.ls_ok = 0;        // alpha_star is not None
+          S.star_has_der = 0; // derphi_star is not None
+          S.zoom_ok = -1;     // -1: no zoom requested, 0/1: zoom arguments ready
+          for (S.w2_i = 0; S.w2_i < 10; ++S.w2_i) {
+            if (S.alpha1 == 0 || S.alpha0 > 1e100) {
+              S.ls_ok = 0;
+              S.star_has_der = 0;
+              break;
+            }
+            if ((S.phi_a1 > S.phi0 + O.c1 * S.alpha1 * S.derphi0) ||
+                ((S.phi_a1 >= S.phi_a0) && S.w2_i > 0)) {
+              S.a_lo = S.alpha0;
+              S.a_hi = S.alpha1;
+              S.phi_lo = S.phi_a0;
+              S.phi_hi = S.phi_a1;
+              S.derphi_lo = S.derphi_a0;
+              S.zoom_ok = 0;
+              break;
+            }
+            VSR_LS_DERPHI(S, O, S.alpha1, S.derphi_a1);
+            if (abs_d(S.derphi_a1) <= -O.c2 * S.derphi0) {
+              S.alpha_star = S.alpha1;
+              S.phi_star = S.phi_a1;
+              S.ls_ok = 1;
+              S.star_has_der = 1;
+              break;
+            }
+            if (S.derphi_a1 >= 0) {
+              S.a_lo = S.alpha1;
+              S.a_hi = S.alpha0;
+              S.phi_lo = S.phi_a1;
+              S.phi_hi = S.phi_a0;
+              S.derphi_lo = S.derphi_a1;
+              S.zoom_ok = 0;
+              break;
+            }
+            {
+              const double alpha2 = min_d(2 * S.alpha1, 1e100);
+              S.alpha0 = S.alpha1;
+              S.alpha1 = alpha2;
+            }
+            S.phi_a0 = S.phi_a1;
+            VSR_LS_PHI(S, O, S.alpha1, S.phi_a1);
+            S.derphi_a0 = S.derphi_a1;
+          }
+          if (S.w2_i >= 10 && S.zoom_ok < 0 && !S.ls_ok) {
+            // for-else: maxiter reached; alpha_star = alpha1, derphi_star = None
+            S.alpha_star = S.alpha1;
+            S.phi_star = S.phi_a1;
+            S.ls_ok = 1;
+            S.star_has_der = 0;
+          }
+          if (S.zoom_ok == 0) {
+            // ---------------- _zoom ----------------
+            S.zi = 0;
+            S.phi_rec = S.phi0;
+            S.a_rec = 0.0;
+            for (;;) {
+              {
+                const double dalpha = S.a_hi - S.a_lo;
+                double a, b;
+                if (dalpha < 0) {
+                  a = S.a_hi;
+                  b = S.a_lo;
+                } else {
+                  a = S.a_lo;
+                  b = S.a_hi;
+                }
+                bool have = false;
+                double aj = 0.0;
+                if (S.zi > 0) {
+                  const double cchk = 0.2 * dalpha;
+                  have = cubicmin(S.a_lo, S.phi_lo, S.derphi_lo, S.a_hi, S.phi_hi, S.a_rec,
+                                  S.phi_rec, aj);
+                  if (have && ((aj > b - cchk) || (aj < a + cchk))) have = false;
+                }
+                if (!have) {
+                  const double qchk = 0.1 * dalpha;
+                  have = quadmin(S.a_lo, S.phi_lo, S.derphi_lo, S.a_hi, S.phi_hi, aj);
+                  if (!have || (aj > b - qchk) || (aj < a + qchk)) aj = S.a_lo + 0.5 * dalpha;
+                }
+                S.a_j = aj;
+              }
+              VSR_LS_PHI(S, O, S.a_j, S.phi_aj);
+              if ((S.phi_aj > S.phi0 + O.c1 * S.a_j * S.derphi0) || (S.phi_aj >= S.phi_lo)) {
+                S.phi_rec = S.phi_hi;
+                S.a_rec = S.a_hi;
+                S.a_hi = S.a_j;
+                S.phi_hi = S.phi_aj;
+              } else {
+                VSR_LS_DERPHI(S, O, S.a_j, S.derphi_aj);
+                if (abs_d(S.derphi_aj) <= -O.c2 * S.derphi0) {
+                  S.alpha_star = S.a_j;
+                  S.phi_star = S.phi_aj;
+                  S.ls_ok = 1;
+                  S.star_has_der = 1;
+                  break;
+                }
+                if (S.derphi_aj * (S.a_hi - S.a_lo) >= 0) {
+                  S.phi_rec = S.phi_hi;
+                  S.a_rec = S.a_hi;
+                  S.a_hi = S.a_lo;
+                  S.phi_hi = S.phi_lo;
+                } else {
+                  S.phi_rec = S.phi_lo;
+                  S.a_rec = S.a_lo;
+                }
+                S.a_lo = S.a_j;
+                S.phi_lo = S.phi_aj;
+                S.derphi_lo = S.derphi_aj;
+              }
+              S.zi += 1;
+              if (S.zi > 10) {
+                S.ls_ok = 0;
+                S.star_has_der = 0;
+                break;
+              }
+            }
+          }
+          if (S.ls_ok) {
+            S.alpha_k = S.alpha_star;
+            S.ls_fval = S.phi_star;
+            S.ls_oldfval = S.phi0;
+            // derphi_star None -> gfkp1 None (recomputed below); else gval[0]
+            if (!S.star_has_der) S.have_gnew = 0;
+          }
+        }
+        if (!S.ls_ok) {
+          S.warnflag = 2;  // _LineSearchError
+          break;
+        }
+        S.old_fval = S.ls_fval;
+        S.old_old_fval = S.ls_oldfval;
+        // xkp1 = xk + alpha_k*pk
+        for (int i = 0; i < k; ++i) {
+          S.Hy[i] = S.alpha_k * S.pk[i];  // sk (kept in Hy until the update below)
+          S.xt[i] = S.xk[i] + S.Hy[i];
+        }
+        if (!S.have_gnew) {
+          VSR_OBJ_SETX(S, S.xt);
+          VSR_OBJ_UPDATE_GRAD(S, O);
+          for (int i = 0; i < k; ++i) S.gnew[i] = S.cg[i];
+          // sk was clobbered? no: Hy is untouched by the objective macros
+        }
+        {
+          // yk = gfkp1 - gfk (stored in gfk's old slot via pk: pk is free now)
+          double gm = 0.0;
+          bool gnan = false;
+          double pn2 = 0.0, xn2 = 0.0;
+          for (int i = 0; i < k; ++i) {
+            pn2 += S.pk[i] * S.pk[i];
+            S.pk[i] = S.gnew[i] - S.gfk[i];  // yk
+            S.gfk[i] = S.gnew[i];
+            S.xk[i] = S.xt[i];
+            xn2 += S.xk[i] * S.xk[i];
+            if (nan_d(S.gfk[i])) gnan = true;
+            if (abs_d(S.gfk[i]) > gm) gm = abs_d(S.gfk[i]);
+          }
+          S.it += 1;
+          S.gnorm = gnan ? ::nan("") : gm;
+          if (S.gnorm <= O.gtol) break;
+          if (S.alpha_k * ::sqrt(pn2) <= O.xrtol * (O.xrtol + ::sqrt(xn2))) break;
+          if (!finite_d(S.old_fval)) {
+            S.warnflag = 2;
+            break;
+          }
+          // BFGS update of the inverse Hessian:
+          //   H <- (I - rho s y^T) H (I - rho y s^T) + rho s s^T
+          // expanded to  H - rho (s (H^T y)^T + (H y) s^T) + (rho^2 y^T H y + rho) s s^T
+          const double* sk = S.Hy;
+          const double* yk = S.pk;
+          double rhok_inv = 0.0;
+          for (int i = 0; i < k; ++i) rhok_inv += yk[i] * sk[i];
+          const double rhok = (rhok_inv == 0.0) ? 1000.0 : 1.0 / rhok_inv;
+          // u = H y, v = H^T y  (H stays symmetric up to rounding; keep both like numpy)
+          double* u = S.gnew;  // free until the next line search
+          double* v = S.xt;    // free until the next line search
+          double yHy = 0.0;
+          for (int i = 0; i < k; ++i) {
+            double a1 = 0.0, a2 = 0.0;
+            for (int j = 0; j < k; ++j) {
+              a1 += S.H[i * k + j] * yk[j];
+              a2 += S.H[j * k + i] * yk[j];
+            }
+            u[i] = a1;
+            v[i] = a2;
+          }
+          for (int i = 0; i < k; ++i) yHy += yk[i] * u[i];
+          const double cs = rhok * rhok * yHy + rhok;
+          for (int i = 0; i < k; ++i)
+            for (int j = 0; j < k; ++j)
+              S.H[i * k + j] += -rhok * (sk[i] * v[j] + u[i] * sk[j]) + cs * sk[i] * sk[j];
+        }
+      }
+      // ---- termination message (_optimize.py:1503-1513) ----
+      {
+        bool xnan = false;
+        for (int i = 0; i < k; ++i)
+          if (nan_d(S.xk[i])) xnan = true;
+        if (S.warnflag == 2)
+          S.status = VSR_FIT_PRECLOSS;
+        else if (S.it >= S.maxiter)
+          S.status = VSR_FIT_MAXITER;
+        else if (nan_d(S.gnorm) || nan_d(S.old_fval) || xnan)
+          S.status = VSR_FIT_NAN;
+        else
+          S.status = VSR_FIT_SUCCESS;
+      }
+      S.pc = -1;
+      return VSR_DONE;
+    default:
+      return VSR_DONE;
+  }
+}
+
+}  // namespace vsr
+
+#endif  // VSR_BFGS_H_
