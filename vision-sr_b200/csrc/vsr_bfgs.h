@@ -677,6 +677,9 @@ VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
         }
         S.old_fval = S.ls_fval;
         S.old_old_fval = S.ls_oldfval;
+#ifdef VSR_TRACE
+        VSR_TRACE(S);
+#endif
         // xkp1 = xk + alpha_k*pk
         for (int i = 0; i < k; ++i) {
           S.Hy[i] = S.alpha_k * S.pk[i];  // sk (kept in Hy until the update below)
@@ -710,32 +713,33 @@ VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
             S.warnflag = 2;
             break;
           }
-          // BFGS update of the inverse Hessian:
-          //   H <- (I - rho s y^T) H (I - rho y s^T) + rho s s^T
-          // expanded to  H - rho (s (H^T y)^T + (H y) s^T) + (rho^2 y^T H y + rho) s s^T
+          // BFGS update of the inverse Hessian (_optimize.py:1496-1499)
+          //   H <- A1 (H A2) + rho s s^T,  A1 = I - rho s y^T,  A2 = I - rho y s^T
+          // evaluated as the two products scipy forms, using their rank-one structure:
+          //   T = H A2      = H - rho (H y) s^T
+          //   A1 T          = T - rho s (y^T T)
           const double* sk = S.Hy;
           const double* yk = S.pk;
           double rhok_inv = 0.0;
           for (int i = 0; i < k; ++i) rhok_inv += yk[i] * sk[i];
           const double rhok = (rhok_inv == 0.0) ? 1000.0 : 1.0 / rhok_inv;
-          // u = H y, v = H^T y  (H stays symmetric up to rounding; keep both like numpy)
           double* u = S.gnew;  // free until the next line search
-          double* v = S.xt;    // free until the next line search
-          double yHy = 0.0;
+          double* w = S.xt;    // free until the next line search
           for (int i = 0; i < k; ++i) {
-            double a1 = 0.0, a2 = 0.0;
-            for (int j = 0; j < k; ++j) {
-              a1 += S.H[i * k + j] * yk[j];
-              a2 += S.H[j * k + i] * yk[j];
-            }
+            double a1 = 0.0;
+            for (int j = 0; j < k; ++j) a1 += S.H[i * k + j] * yk[j];
             u[i] = a1;
-            v[i] = a2;
           }
-          for (int i = 0; i < k; ++i) yHy += yk[i] * u[i];
-          const double cs = rhok * rhok * yHy + rhok;
+          for (int i = 0; i < k; ++i)
+            for (int j = 0; j < k; ++j) S.H[i * k + j] -= rhok * u[i] * sk[j];
+          for (int j = 0; j < k; ++j) {
+            double a2 = 0.0;
+            for (int l = 0; l < k; ++l) a2 += yk[l] * S.H[l * k + j];
+            w[j] = a2;
+          }
           for (int i = 0; i < k; ++i)
             for (int j = 0; j < k; ++j)
-              S.H[i * k + j] += -rhok * (sk[i] * v[j] + u[i] * sk[j]) + cs * sk[i] * sk[j];
+              S.H[i * k + j] += rhok * sk[i] * sk[j] - rhok * sk[i] * w[j];
         }
       }
       // ---- termination message (_optimize.py:1503-1513) ----
