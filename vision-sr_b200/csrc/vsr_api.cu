@@ -1,0 +1,697 @@
+// vsr_api.cu -- C ABI of libvsr.so (declared in include/vsr.h): handle, uploads, launch
+// logic.  No torch types, no host synchronisation except in the *_host entry points.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/vsr.h"
+#include "vsr_kernels.cuh"
+
+namespace {
+
+constexpr int kWidths[] = {0, 1, 2, 3, 4, 6, 8, 12, 16};
+constexpr int kNumWidths = sizeof(kWidths) / sizeof(kWidths[0]);
+
+int pick_width(int k) {
+  for (int w : kWidths)
+    if (w >= k) return w;
+  return -1;
+}
+
+std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);  // synchronises: nothing in flight can still use the old block
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max(bytes, (size_t)4096);
+    want = (want * 3) / 2;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaEvent_t done = nullptr;  // last async copy that read from this buffer
+  cudaError_t reserve(size_t bytes) {
+    if (done) cudaEventSynchronize(done);
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max(bytes, (size_t)4096) * 2;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    if (!done) cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+    return e;
+  }
+  void release() {
+    if (done) {
+      cudaEventSynchronize(done);
+      cudaEventDestroy(done);
+    }
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    done = nullptr;
+  }
+};
+
+struct PointSlot {
+  const void* X = nullptr;
+  const void* y = nullptr;
+  int64_t n = 0, ldx = 0;
+  int n_vars = 0;
+  DevBuf ownX, ownY;
+};
+
+}  // namespace
+
+struct vsr_handle {
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  PointSlot pts[2];
+  // programs
+  DevBuf d_insns, d_insn_off, d_imms, d_imm_off, d_k;
+  std::vector<int32_t> h_k, h_ninsn, h_nimm;
+  int n_programs = 0;
+  // scratch
+  DevBuf d_lists;    // grouped run / pair lists
+  DevBuf d_partial;  // eval partial sums
+  DevBuf d_stage;    // device staging of the *_host entry points
+  PinnedBuf h_lists;
+  int64_t launches = 0;
+};
+
+namespace {
+
+int fail(vsr_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h)
+    h->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define VSR_CUDA(h, expr)                                                              \
+  do {                                                                                 \
+    cudaError_t e_ = (expr);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return fail(h, VSR_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                 \
+  } while (0)
+
+vsr::ProgramTable table_of(const vsr_handle* h) {
+  vsr::ProgramTable t;
+  t.insns = (const vsr_insn_t*)h->d_insns.p;
+  t.insn_off = (const int32_t*)h->d_insn_off.p;
+  t.imms = (const double*)h->d_imms.p;
+  t.imm_off = (const int32_t*)h->d_imm_off.p;
+  t.k = (const int32_t*)h->d_k.p;
+  return t;
+}
+
+vsr::Points points_of(const PointSlot& s) {
+  vsr::Points p;
+  p.X = s.X;
+  p.y = s.y;
+  p.n = s.n;
+  p.ldx = s.ldx;
+  return p;
+}
+
+// points per thread for a tangent width: wide duals are register hungry
+constexpr int points_per_thread(int K) { return K <= 4 ? 2 : 1; }
+
+template <typename T, int K>
+cudaError_t launch_fit_T(const vsr::FitArgs& a, int threads, size_t smem, cudaStream_t st) {
+  constexpr int P = points_per_thread(K);
+  auto kern = vsr::fit_kernel<T, K, P>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<a.n_runs, threads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_fit(int K, const vsr::FitArgs& a, int threads, size_t smem, cudaStream_t st) {
+  switch (K) {
+#define C(KK) case KK: return launch_fit_T<T, KK>(a, threads, smem, st);
+    C(0) C(1) C(2) C(3) C(4) C(6) C(8) C(12) C(16)
+#undef C
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <typename T, int K>
+cudaError_t launch_eval_T(const vsr::EvalArgs& a, int threads, size_t smem, cudaStream_t st) {
+  constexpr int P = points_per_thread(K);
+  auto kern = vsr::eval_kernel<T, K, P>;
+  dim3 grid(a.n_pairs, a.nsplit);
+  kern<<<grid, threads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_eval(int K, const vsr::EvalArgs& a, int threads, size_t smem, cudaStream_t st) {
+  switch (K) {
+#define C(KK) case KK: return launch_eval_T<T, KK>(a, threads, smem, st);
+    C(0) C(1) C(2) C(3) C(4) C(6) C(8) C(12) C(16)
+#undef C
+  }
+  return cudaErrorInvalidValue;
+}
+
+int next_pow2(int64_t v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// warps per run: enough lanes that a sweep is a handful of tile iterations, more when
+// there are too few runs to fill 148 SMs
+int choose_warps(const vsr_handle* h, int64_t N, int n_runs, int P, int forced) {
+  if (forced > 0) return std::min(8, std::max(1, forced));
+  int w = std::min<int64_t>(8, std::max<int64_t>(1, next_pow2((N + 32 * P * 4 - 1) / (32 * P * 4))));
+  while (w < 8 && (int64_t)n_runs * w < (int64_t)h->num_sms * 16 && N / (32 * P * w) >= 2) w <<= 1;
+  return w;
+}
+
+struct Group {
+  int K;
+  int grad_mode;
+  std::vector<int32_t> prog, slot;
+  int kmax = 0, max_insn = 0, max_imm = 0;
+};
+
+// copies host int32 lists into the handle's device list buffer at `offset` (in ints)
+int stage_lists(vsr_handle* h, const std::vector<int32_t>& all, cudaStream_t st) {
+  const size_t bytes = all.size() * sizeof(int32_t);
+  VSR_CUDA(h, h->h_lists.reserve(bytes));
+  VSR_CUDA(h, h->d_lists.reserve(bytes));
+  std::memcpy(h->h_lists.p, all.data(), bytes);
+  VSR_CUDA(h, cudaMemcpyAsync(h->d_lists.p, h->h_lists.p, bytes, cudaMemcpyHostToDevice, st));
+  VSR_CUDA(h, cudaEventRecord(h->h_lists.done, st));
+  return VSR_OK;
+}
+
+// eval over explicit (prog, row, out) triples, all of one tangent width
+int run_eval_group(vsr_handle* h, int K, int dtype, const int32_t* d_prog, const int32_t* d_row,
+                   const int32_t* d_out, int n_pairs, int kmax, int max_insn, int max_imm,
+                   const double* consts, int kstride, double* out_loss, double* out_grad,
+                   cudaStream_t st) {
+  const PointSlot& ps = h->pts[dtype];
+  const int P = points_per_thread(K);
+  const int64_t N = ps.n;
+  int threads = 32 * std::min<int64_t>(8, std::max<int64_t>(1, next_pow2((N + 32 * P * 4 - 1) / (32 * P * 4))));
+  const int64_t tile = (int64_t)threads * P;
+  const int64_t tiles = (N + tile - 1) / tile;
+  // split the points when there are too few pairs to fill the machine
+  int nsplit = 1;
+  const int64_t target = (int64_t)h->num_sms * 8;
+  if (n_pairs < target) nsplit = (int)std::min<int64_t>(std::max<int64_t>(1, tiles / 8), (target + n_pairs - 1) / n_pairs);
+  nsplit = std::max(1, std::min(nsplit, 65535));
+  VSR_CUDA(h, h->d_partial.reserve((size_t)n_pairs * nsplit * (K + 1) * sizeof(double)));
+  vsr::EvalArgs a;
+  a.pt = table_of(h);
+  a.pts = points_of(ps);
+  a.pair_prog = d_prog;
+  a.pair_row = d_row;
+  a.pair_out = d_out;
+  a.n_pairs = n_pairs;
+  a.kstride = kstride;
+  a.consts = consts;
+  a.partial = (double*)h->d_partial.p;
+  a.nsplit = nsplit;
+  const int nw = threads / 32;
+  const size_t smem = sizeof(double) * (size_t)(nw * (K + 1) + kmax + 2 + max_imm + max_insn);
+  cudaError_t e = dtype == VSR_F64 ? launch_eval<double>(K, a, threads, smem, st)
+                                   : launch_eval<float>(K, a, threads, smem, st);
+  if (e != cudaSuccess) return fail(h, VSR_ECUDA, "eval kernel launch failed: %s", cudaGetErrorString(e));
+  const int total = n_pairs * (K + 1);
+  vsr::eval_finalize<<<(total + 127) / 128, 128, 0, st>>>(
+      a.partial, d_prog, d_out, a.pt.k, n_pairs, nsplit, K, kstride, 1.0 / (double)N, out_loss,
+      out_grad);
+  VSR_CUDA(h, cudaGetLastError());
+  h->launches += 2;
+  return VSR_OK;
+}
+
+int check_ready(vsr_handle* h, int dtype) {
+  if (!h) return VSR_EINVAL;
+  if (dtype != VSR_F64 && dtype != VSR_F32) return fail(h, VSR_EINVAL, "dtype must be VSR_F64 or VSR_F32");
+  if (h->n_programs <= 0) return fail(h, VSR_ESTATE, "no programs uploaded");
+  if (!h->pts[dtype].X || h->pts[dtype].n <= 0)
+    return fail(h, VSR_ESTATE, "no points uploaded for dtype %d", dtype);
+  return VSR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vsr_abi_version(void) { return VSR_ABI_VERSION; }
+
+void vsr_fit_opts_default(vsr_fit_opts* o) {
+  if (!o) return;
+  o->gtol = 1e-5;
+  o->c1 = 1e-4;
+  o->c2 = 0.9;
+  o->xrtol = 0.0;
+  o->fd_eps = 1.4901161193847656e-08;
+  o->penalty = 1e6;
+  o->loss_scale = 1.0;
+  o->stop_time = 1e9;
+  o->maxiter_per_k = 200;
+  o->grad_mode = VSR_GRAD_DUAL;
+  o->eval_dtype = VSR_F64;
+  o->score_dtype = VSR_F64;
+  o->warps_per_run = 0;
+  o->reserved = 0;
+}
+
+int vsr_create(int device, vsr_handle** out) {
+  if (!out) return VSR_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return fail(nullptr, VSR_ECUDA, "no CUDA device (%s); libvsr has no CPU path",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(nullptr, VSR_EINVAL, "device %d out of range [0,%d)", device, count);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, VSR_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, VSR_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, VSR_ECUDA, "device %d is sm_%d%d; libvsr is built for sm_100a only", device,
+                prop.major, prop.minor);
+  vsr_handle* h = new (std::nothrow) vsr_handle();
+  if (!h) return fail(nullptr, VSR_ENOMEM, "out of host memory");
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;
+  return VSR_OK;
+}
+
+void vsr_destroy(vsr_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (auto& s : h->pts) {
+    s.ownX.release();
+    s.ownY.release();
+  }
+  h->d_insns.release();
+  h->d_insn_off.release();
+  h->d_imms.release();
+  h->d_imm_off.release();
+  h->d_k.release();
+  h->d_lists.release();
+  h->d_partial.release();
+  h->d_stage.release();
+  h->h_lists.release();
+  delete h;
+}
+
+const char* vsr_last_error(const vsr_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t vsr_launch_count(const vsr_handle* h) { return h ? h->launches : 0; }
+
+int vsr_set_points(vsr_handle* h, const void* X_dev, const void* y_dev, int64_t n_points,
+                   int64_t ldx, int32_t n_vars, int32_t dtype) {
+  if (!h) return VSR_EINVAL;
+  if (dtype != VSR_F64 && dtype != VSR_F32) return fail(h, VSR_EINVAL, "bad dtype %d", dtype);
+  if (!X_dev || !y_dev || n_points <= 0 || ldx < n_points || n_vars < 1 || n_vars > VSR_MAX_VARS)
+    return fail(h, VSR_EINVAL, "bad points: n=%lld ldx=%lld n_vars=%d", (long long)n_points,
+                (long long)ldx, n_vars);
+  PointSlot& s = h->pts[dtype];
+  s.X = X_dev;
+  s.y = y_dev;
+  s.n = n_points;
+  s.ldx = ldx;
+  s.n_vars = n_vars;
+  return VSR_OK;
+}
+
+int vsr_upload_points(vsr_handle* h, const void* X_host, const void* y_host, int64_t n_points,
+                      int64_t ldx, int32_t n_vars, int32_t dtype, void* stream) {
+  if (!h) return VSR_EINVAL;
+  if (dtype != VSR_F64 && dtype != VSR_F32) return fail(h, VSR_EINVAL, "bad dtype %d", dtype);
+  if (!X_host || !y_host || n_points <= 0 || ldx < n_points || n_vars < 1 || n_vars > VSR_MAX_VARS)
+    return fail(h, VSR_EINVAL, "bad points: n=%lld ldx=%lld n_vars=%d", (long long)n_points,
+                (long long)ldx, n_vars);
+  cudaStream_t st = (cudaStream_t)stream;
+  VSR_CUDA(h, cudaSetDevice(h->device));
+  const size_t es = dtype == VSR_F64 ? 8 : 4;
+  PointSlot& s = h->pts[dtype];
+  // device copy keeps columns 16-byte aligned: pad the column stride to a multiple of 4
+  const int64_t dld = (n_points + 3) & ~(int64_t)3;
+  VSR_CUDA(h, s.ownX.reserve((size_t)dld * n_vars * es));
+  VSR_CUDA(h, s.ownY.reserve((size_t)dld * es));
+  VSR_CUDA(h, cudaMemcpy2DAsync(s.ownX.p, dld * es, X_host, ldx * es, n_points * es, n_vars,
+                                cudaMemcpyHostToDevice, st));
+  VSR_CUDA(h, cudaMemcpyAsync(s.ownY.p, y_host, n_points * es, cudaMemcpyHostToDevice, st));
+  s.X = s.ownX.p;
+  s.y = s.ownY.p;
+  s.n = n_points;
+  s.ldx = dld;
+  s.n_vars = n_vars;
+  return VSR_OK;
+}
+
+int vsr_upload_programs(vsr_handle* h, const uint64_t* insns, const int32_t* insn_off,
+                        const double* imms, const int32_t* imm_off, const int32_t* k,
+                        int32_t n_programs, void* stream) {
+  if (!h) return VSR_EINVAL;
+  if (!insns || !insn_off || !imms || !imm_off || !k || n_programs <= 0)
+    return fail(h, VSR_EINVAL, "bad program table");
+  cudaStream_t st = (cudaStream_t)stream;
+  VSR_CUDA(h, cudaSetDevice(h->device));
+  h->n_programs = 0;
+  h->h_k.assign(k, k + n_programs);
+  h->h_ninsn.resize(n_programs);
+  h->h_nimm.resize(n_programs);
+  for (int c = 0; c < n_programs; ++c) {
+    const int ni = insn_off[c + 1] - insn_off[c];
+    const int nm = imm_off[c + 1] - imm_off[c];
+    if (ni < 1 || ni > VSR_MAX_INSNS || nm < 0 || nm > VSR_MAX_IMMS || k[c] < 0 || k[c] > VSR_MAX_CONSTS)
+      return fail(h, VSR_ELIMIT, "program %d: %d insns, %d literals, %d constants", c, ni, nm, k[c]);
+    if (VSR_OP(insns[insn_off[c + 1] - 1]) != VSR_END)
+      return fail(h, VSR_EINVAL, "program %d does not end in END", c);
+    // static check of operand indices and stack discipline: the kernels trust the table
+    int sp = 0;
+    for (int i = insn_off[c]; i < insn_off[c + 1]; ++i) {
+      const unsigned op = VSR_OP(insns[i]), src = VSR_SRC(insns[i]), idx = VSR_IDX(insns[i]);
+      if (op >= VSR_OP_COUNT) return fail(h, VSR_EINVAL, "program %d: bad opcode %u", c, op);
+      if (op == VSR_PUSH && ++sp > VSR_MAX_STACK) return fail(h, VSR_ELIMIT, "program %d: stack too deep", c);
+      if (op >= VSR_LOAD && op <= VSR_RPOW && op != VSR_PUSH) {
+        if (src == VSR_SRC_STACK) {
+          if (--sp < 0) return fail(h, VSR_EINVAL, "program %d: stack underflow", c);
+        } else if (src == VSR_SRC_VAR) {
+          if (idx >= VSR_MAX_VARS) return fail(h, VSR_EINVAL, "program %d: variable %u", c, idx);
+        } else if (src == VSR_SRC_CONST) {
+          if ((int)idx >= k[c]) return fail(h, VSR_EINVAL, "program %d: constant %u of %d", c, idx, k[c]);
+        } else if (src == VSR_SRC_IMM) {
+          if ((int)idx >= nm) return fail(h, VSR_EINVAL, "program %d: literal %u of %d", c, idx, nm);
+        } else {
+          return fail(h, VSR_EINVAL, "program %d: bad operand source %u", c, src);
+        }
+      }
+    }
+    h->h_ninsn[c] = ni;
+    h->h_nimm[c] = nm;
+  }
+  const size_t nins = insn_off[n_programs], nimm = std::max(1, imm_off[n_programs]);
+  VSR_CUDA(h, h->d_insns.reserve(nins * sizeof(uint64_t)));
+  VSR_CUDA(h, h->d_insn_off.reserve((n_programs + 1) * sizeof(int32_t)));
+  VSR_CUDA(h, h->d_imms.reserve(nimm * sizeof(double)));
+  VSR_CUDA(h, h->d_imm_off.reserve((n_programs + 1) * sizeof(int32_t)));
+  VSR_CUDA(h, h->d_k.reserve(n_programs * sizeof(int32_t)));
+  // pageable sources: cudaMemcpyAsync stages them before returning
+  VSR_CUDA(h, cudaMemcpyAsync(h->d_insns.p, insns, nins * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  VSR_CUDA(h, cudaMemcpyAsync(h->d_insn_off.p, insn_off, (n_programs + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (imm_off[n_programs] > 0)
+    VSR_CUDA(h, cudaMemcpyAsync(h->d_imms.p, imms, imm_off[n_programs] * sizeof(double), cudaMemcpyHostToDevice, st));
+  VSR_CUDA(h, cudaMemcpyAsync(h->d_imm_off.p, imm_off, (n_programs + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  VSR_CUDA(h, cudaMemcpyAsync(h->d_k.p, k, n_programs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  h->n_programs = n_programs;
+  return VSR_OK;
+}
+
+int vsr_eval(vsr_handle* h, const int32_t* prog_idx, const int32_t* const_row, int32_t n_pairs,
+             const double* consts, int32_t kstride, int32_t dtype, double* out_loss,
+             double* out_grad, void* stream) {
+  int rc = check_ready(h, dtype);
+  if (rc) return rc;
+  if (!prog_idx || n_pairs <= 0 || !out_loss || kstride < 0 || (!consts && kstride > 0))
+    return fail(h, VSR_EINVAL, "bad eval arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  VSR_CUDA(h, cudaSetDevice(h->device));
+  // group pairs by tangent width (value only: one group of width 0)
+  std::vector<Group> groups(kNumWidths + 1);
+  for (int i = 0; i < kNumWidths; ++i) groups[i].K = kWidths[i];
+  Group& toowide = groups[kNumWidths];
+  for (int p = 0; p < n_pairs; ++p) {
+    const int c = prog_idx[p];
+    if (c < 0 || c >= h->n_programs) return fail(h, VSR_EINVAL, "pair %d: program %d out of range", p, c);
+    const int k = h->h_k[c];
+    if (k > kstride) return fail(h, VSR_EINVAL, "pair %d: %d constants > kstride %d", p, k, kstride);
+    int gi = 0;
+    if (out_grad) {
+      const int w = pick_width(k);
+      if (w < 0) {
+        toowide.prog.push_back(p);
+        gi = 0;  // value through the width-0 kernel, gradient row = nan
+      } else {
+        gi = (int)(std::find(kWidths, kWidths + kNumWidths, w) - kWidths);
+      }
+    }
+    Group& g = groups[gi];
+    g.prog.push_back(c);
+    g.slot.push_back(const_row ? const_row[p] : p);  // row of consts
+    g.kmax = std::max(g.kmax, k);
+    g.max_insn = std::max(g.max_insn, h->h_ninsn[c]);
+    g.max_imm = std::max(g.max_imm, h->h_nimm[c]);
+    // output row rides in a third list
+    (void)0;
+  }
+  // lists: for each group prog | row | out
+  std::vector<int32_t> all;
+  std::vector<size_t> off(kNumWidths + 1, 0);
+  std::vector<std::vector<int32_t>> outs(kNumWidths);
+  {
+    // recompute output rows per group in the same order as above
+    std::vector<int> cursor(kNumWidths, 0);
+    for (auto& o : outs) o.clear();
+    for (int p = 0; p < n_pairs; ++p) {
+      const int k = h->h_k[prog_idx[p]];
+      int gi = 0;
+      if (out_grad) {
+        const int w = pick_width(k);
+        if (w >= 0) gi = (int)(std::find(kWidths, kWidths + kNumWidths, w) - kWidths);
+      }
+      outs[gi].push_back(p);
+    }
+  }
+  for (int gi = 0; gi < kNumWidths; ++gi) {
+    off[gi] = all.size();
+    Group& g = groups[gi];
+    all.insert(all.end(), g.prog.begin(), g.prog.end());
+    all.insert(all.end(), g.slot.begin(), g.slot.end());
+    all.insert(all.end(), outs[gi].begin(), outs[gi].end());
+  }
+  off[kNumWidths] = all.size();
+  all.insert(all.end(), toowide.prog.begin(), toowide.prog.end());
+  rc = stage_lists(h, all, st);
+  if (rc) return rc;
+  const int32_t* dl = (const int32_t*)h->d_lists.p;
+  for (int gi = 0; gi < kNumWidths; ++gi) {
+    Group& g = groups[gi];
+    const int n = (int)g.prog.size();
+    if (!n) continue;
+    rc = run_eval_group(h, g.K, dtype, dl + off[gi], dl + off[gi] + n, dl + off[gi] + 2 * n, n,
+                        g.kmax, g.max_insn, g.max_imm, consts, kstride, out_loss,
+                        g.K > 0 ? out_grad : nullptr, st);
+    if (rc) return rc;
+  }
+  if (out_grad && !toowide.prog.empty()) {
+    const int n = (int)toowide.prog.size();
+    vsr::fill_nan_rows<<<(n * kstride + 127) / 128, 128, 0, st>>>(dl + off[kNumWidths], n, kstride, out_grad);
+    VSR_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+  }
+  if (out_grad) {
+    // width-0 pairs (k == 0) have no gradient entries to write
+  }
+  return VSR_OK;
+}
+
+int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int32_t n_runs,
+            const double* x0, int32_t kstride, const vsr_fit_opts* opts, double* out_consts,
+            double* out_lastx, double* out_loss, double* out_final_mse, int32_t* out_info,
+            void* stream) {
+  if (!h || !opts) return VSR_EINVAL;
+  int rc = check_ready(h, opts->eval_dtype);
+  if (rc) return rc;
+  rc = check_ready(h, opts->score_dtype);
+  if (rc) return rc;
+  if (!run_prog || !run_slot || n_runs <= 0 || !x0 || kstride < 1 || !out_consts || !out_lastx ||
+      !out_loss || !out_final_mse || !out_info)
+    return fail(h, VSR_EINVAL, "bad fit arguments");
+  if (opts->grad_mode != VSR_GRAD_DUAL && opts->grad_mode != VSR_GRAD_FD)
+    return fail(h, VSR_EINVAL, "bad grad_mode %d", opts->grad_mode);
+  cudaStream_t st = (cudaStream_t)stream;
+  VSR_CUDA(h, cudaSetDevice(h->device));
+
+  // group runs: (tangent width, gradient mode).  k == 0 and FD runs use the width-0 kernel.
+  std::vector<Group> groups;
+  auto group_of = [&](int K, int mode) -> Group& {
+    for (auto& g : groups)
+      if (g.K == K && g.grad_mode == mode) return g;
+    groups.emplace_back();
+    groups.back().K = K;
+    groups.back().grad_mode = mode;
+    return groups.back();
+  };
+  for (int r = 0; r < n_runs; ++r) {
+    const int c = run_prog[r];
+    if (c < 0 || c >= h->n_programs) return fail(h, VSR_EINVAL, "run %d: program %d out of range", r, c);
+    const int k = h->h_k[c];
+    if (k > kstride) return fail(h, VSR_EINVAL, "run %d: %d constants > kstride %d", r, k, kstride);
+    int mode = opts->grad_mode, K = 0;
+    if (k > 0 && mode == VSR_GRAD_DUAL) {
+      K = pick_width(k);
+      if (K < 0) {  // more constants than the widest dual kernel: forward differences
+        K = 0;
+        mode = VSR_GRAD_FD;
+      }
+    }
+    if (k == 0) mode = VSR_GRAD_DUAL;
+    Group& g = group_of(K, mode);
+    g.prog.push_back(c);
+    g.slot.push_back(run_slot[r]);
+    g.kmax = std::max(g.kmax, k);
+    g.max_insn = std::max(g.max_insn, h->h_ninsn[c]);
+    g.max_imm = std::max(g.max_imm, h->h_nimm[c]);
+  }
+  // longest programs first inside a group so the tail of the launch is short runs
+  for (auto& g : groups) {
+    std::vector<int> order(g.prog.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      return h->h_ninsn[g.prog[a]] * (1 + h->h_k[g.prog[a]]) > h->h_ninsn[g.prog[b]] * (1 + h->h_k[g.prog[b]]);
+    });
+    std::vector<int32_t> p2(order.size()), s2(order.size());
+    for (size_t i = 0; i < order.size(); ++i) {
+      p2[i] = g.prog[order[i]];
+      s2[i] = g.slot[order[i]];
+    }
+    g.prog.swap(p2);
+    g.slot.swap(s2);
+  }
+  // lists: per group prog | slot ; then for the final score: prog | slot | slot
+  std::vector<int32_t> all;
+  std::vector<size_t> off;
+  for (auto& g : groups) {
+    off.push_back(all.size());
+    all.insert(all.end(), g.prog.begin(), g.prog.end());
+    all.insert(all.end(), g.slot.begin(), g.slot.end());
+  }
+  const size_t score_off = all.size();
+  int s_kmax = 0, s_insn = 0, s_imm = 0;
+  for (int r = 0; r < n_runs; ++r) all.push_back(run_prog[r]);
+  for (int r = 0; r < n_runs; ++r) all.push_back(run_slot[r]);
+  for (int r = 0; r < n_runs; ++r) {
+    const int c = run_prog[r];
+    s_kmax = std::max(s_kmax, h->h_k[c]);
+    s_insn = std::max(s_insn, h->h_ninsn[c]);
+    s_imm = std::max(s_imm, h->h_nimm[c]);
+  }
+  rc = stage_lists(h, all, st);
+  if (rc) return rc;
+  const int32_t* dl = (const int32_t*)h->d_lists.p;
+
+  const PointSlot& ps = h->pts[opts->eval_dtype];
+  for (size_t gi = 0; gi < groups.size(); ++gi) {
+    Group& g = groups[gi];
+    const int n = (int)g.prog.size();
+    vsr::FitArgs a;
+    a.pt = table_of(h);
+    a.pts = points_of(ps);
+    a.run_prog = dl + off[gi];
+    a.run_slot = dl + off[gi] + n;
+    a.n_runs = n;
+    a.kstride = kstride;
+    a.x0 = x0;
+    a.out_consts = out_consts;
+    a.out_lastx = out_lastx;
+    a.out_loss = out_loss;
+    a.out_info = out_info;
+    a.O.gtol = opts->gtol;
+    a.O.c1 = opts->c1;
+    a.O.c2 = opts->c2;
+    a.O.xrtol = opts->xrtol;
+    a.O.fd_eps = opts->fd_eps;
+    a.O.penalty = opts->penalty;
+    a.O.loss_scale = opts->loss_scale;
+    a.O.stop_time = opts->stop_time;
+    a.O.maxiter_per_k = opts->maxiter_per_k;
+    a.O.grad_mode = g.grad_mode;
+    const int P = points_per_thread(g.K);
+    const int warps = g.kmax == 0 ? 1 : choose_warps(h, ps.n, n, P, opts->warps_per_run);
+    const size_t smem = sizeof(double) * (size_t)vsr::fit_smem_doubles(g.kmax, g.K, warps, g.max_insn, g.max_imm);
+    cudaError_t e = opts->eval_dtype == VSR_F64 ? launch_fit<double>(g.K, a, warps * 32, smem, st)
+                                                : launch_fit<float>(g.K, a, warps * 32, smem, st);
+    if (e != cudaSuccess) return fail(h, VSR_ECUDA, "fit kernel launch failed: %s", cudaGetErrorString(e));
+    h->launches += 1;
+  }
+  // per-restart score: plain MSE at the last evaluated point, in score_dtype (bfgs.py:120-132)
+  rc = run_eval_group(h, 0, opts->score_dtype, dl + score_off, dl + score_off + n_runs,
+                      dl + score_off + n_runs, n_runs, s_kmax, s_insn, s_imm, out_lastx, kstride,
+                      out_final_mse, nullptr, st);
+  return rc;
+}
+
+int vsr_fit_host(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int32_t n_runs,
+                 int32_t n_slots, const double* x0, int32_t kstride, const vsr_fit_opts* opts,
+                 double* out_consts, double* out_lastx, double* out_loss, double* out_final_mse,
+                 int32_t* out_info, void* stream) {
+  if (!h) return VSR_EINVAL;
+  if (n_slots <= 0 || kstride < 1 || !x0 || !out_consts || !out_lastx || !out_loss ||
+      !out_final_mse || !out_info)
+    return fail(h, VSR_EINVAL, "bad fit_host arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  VSR_CUDA(h, cudaSetDevice(h->device));
+  const size_t row = (size_t)kstride * sizeof(double);
+  const size_t b_x = (size_t)n_slots * row;
+  const size_t b_s = (size_t)n_slots * sizeof(double);
+  const size_t b_i = (size_t)n_slots * 4 * sizeof(int32_t);
+  VSR_CUDA(h, h->d_stage.reserve(3 * b_x + 2 * b_s + b_i));
+  char* base = (char*)h->d_stage.p;
+  double* d_x0 = (double*)base;
+  double* d_c = (double*)(base + b_x);
+  double* d_l = (double*)(base + 2 * b_x);
+  double* d_loss = (double*)(base + 3 * b_x);
+  double* d_mse = (double*)(base + 3 * b_x + b_s);
+  int32_t* d_info = (int32_t*)(base + 3 * b_x + 2 * b_s);
+  VSR_CUDA(h, cudaMemcpyAsync(d_x0, x0, b_x, cudaMemcpyHostToDevice, st));
+  // slots no run touches come back as nan / NOT_RUN
+  VSR_CUDA(h, cudaMemsetAsync(d_c, 0xff, 2 * b_x + 2 * b_s, st));
+  VSR_CUDA(h, cudaMemsetAsync(d_info, 0xff, b_i, st));
+  int rc = vsr_fit(h, run_prog, run_slot, n_runs, d_x0, kstride, opts, d_c, d_l, d_loss, d_mse,
+                   d_info, stream);
+  if (rc) return rc;
+  VSR_CUDA(h, cudaMemcpyAsync(out_consts, d_c, b_x, cudaMemcpyDeviceToHost, st));
+  VSR_CUDA(h, cudaMemcpyAsync(out_lastx, d_l, b_x, cudaMemcpyDeviceToHost, st));
+  VSR_CUDA(h, cudaMemcpyAsync(out_loss, d_loss, b_s, cudaMemcpyDeviceToHost, st));
+  VSR_CUDA(h, cudaMemcpyAsync(out_final_mse, d_mse, b_s, cudaMemcpyDeviceToHost, st));
+  VSR_CUDA(h, cudaMemcpyAsync(out_info, d_info, b_i, cudaMemcpyDeviceToHost, st));
+  VSR_CUDA(h, cudaStreamSynchronize(st));
+  return VSR_OK;
+}
+
+}  // extern "C"

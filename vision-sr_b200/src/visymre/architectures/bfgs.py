@@ -1,0 +1,284 @@
+"""Constant fitting of beam candidates on the B200 (drop-in for the reference module).
+
+Same entry point, arguments, return value and quirks as reference
+``src/visymre/architectures/bfgs.py`` (``bfgs`` :42-215; the step labels Q1..Q13 below
+are SURVEY.md section 3.3), but nothing is evaluated on the CPU: the skeleton is
+compiled to bytecode (``engine/compiler.py``) and every restart of every candidate is
+optimised by one CUDA launch (``csrc/vsr_kernels.cuh``).  ``bfgs_batch`` is the native
+shape of the work -- all candidates of a beam at once -- and ``bfgs`` is the
+single-candidate view of it that ``hlsc.py:410`` and ``model.py:16`` call.
+
+Extra, optional knobs read with ``getattr(cfg.bfgs, name, default)`` (the reference's
+config.yaml does not have them, so drivers keep working unchanged):
+  grad_mode   "dual" (default; exact forward-mode gradients) or "fd" (scipy's 2-point
+              forward differences, reproduces the reference's trajectories)
+  precision   "fp64" (default, what the reference's loss uses) or "fp32"
+  prune_threshold / prune_tolerance   as in the reference (bfgs.py:143-144)
+"""
+import re
+
+import numpy as np
+import sympy as sp
+import torch
+
+from ..dataset.generator import Generator
+from ..engine import fitter, isa
+from ..engine.compiler import CompileError, compile_sympy
+from . import data
+
+
+def replace_illegal_variables(expr, max_var=5):
+    """Q4 (bfgs.py:11-21): rename x_i to x_{i-1} when x_{i-1} does not occur, i = 2..5."""
+    present = set(re.findall(r"x_\d+", expr))
+    if "x_0" in present:
+        raise ValueError(f"illegal variable x_0 in expression:\n{expr}")
+    fixed = expr
+    for i in range(2, max_var + 1):
+        if f"x_{i}" in present and f"x_{i - 1}" not in present:
+            fixed = re.sub(rf"\bx_{i}\b", f"x_{i - 1}", fixed)
+    return fixed
+
+
+def _opt(cfg, name, default=None):
+    b = cfg.bfgs if hasattr(cfg, "bfgs") else cfg["bfgs"]
+    try:
+        return getattr(b, name)
+    except (AttributeError, KeyError):
+        pass
+    try:
+        return b[name]
+    except (KeyError, TypeError, IndexError):
+        return default
+
+
+def skeleton_string(pred_str, cfg, test_data):
+    """Q1-Q5: token ids (leading S included) -> (c-named infix string, k)."""
+    if isinstance(pred_str, list):
+        pred_str = np.array(pred_str)
+    if isinstance(pred_str, torch.Tensor):
+        pred_str = pred_str.detach().cpu().numpy()
+    ids = np.asarray(pred_str)[1:].tolist()
+    raw = data.de_tokenize(ids, test_data.id2word)
+    if _opt(cfg, "add_coefficients_if_not_existing", False) and "constant" not in raw:
+        # The reference's branch (bfgs.py:52-64) hands the tuple returned by
+        # constants_to_placeholder to sympy_to_prefix and always raises
+        # UnknownSymPyOperator; its wrapper then drops the candidate.  Same outcome here.
+        from ..dataset.generator import UnknownSymPyOperator
+        raise UnknownSymPyOperator("add_coefficients_if_not_existing is broken in the reference")
+    candidate = Generator.prefix_to_infix(raw, coefficients=["constant"],
+                                          variables=test_data.total_variables)
+    candidate = replace_illegal_variables(candidate.format(constant="constant"))
+    k = candidate.count("constant")
+    expr = candidate
+    for i in range(k):
+        expr = expr.replace("constant", f"c{i}", 1)
+    return expr, k
+
+
+class _Candidate:
+    __slots__ = ("expr", "k", "prog", "error")
+
+    def __init__(self):
+        self.expr = self.prog = self.error = None
+        self.k = 0
+
+
+def _engine_opts(cfg, scale, eval_dtype, score_dtype):
+    mode = str(_opt(cfg, "grad_mode", "dual")).lower()
+    return fitter.default_opts(
+        loss_scale=scale,
+        stop_time=float(_opt(cfg, "stop_time", 1e9)),
+        grad_mode=isa.GRAD_MODE["VSR_GRAD_FD" if mode == "fd" else "VSR_GRAD_DUAL"],
+        eval_dtype=eval_dtype, score_dtype=score_dtype)
+
+
+def _substitute(expr, symbols, values):
+    """bfgs.py:120-124: put the numbers in, one constant after the other."""
+    final = expr
+    for s, v in zip(symbols, values):
+        final = sp.sympify(final).replace(s, v)
+    return final
+
+
+def bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
+    """Fit every candidate of a beam in one go.
+
+    Returns a list with one entry per candidate: the reference's 4-tuple
+    ``(best_expr_str, best_consts, best_loss, expr)`` or the ``Exception`` that
+    ``bfgs()`` would have raised for it.  ``x0``: optional list (one per candidate) of
+    ``[R, k]`` starting points; default is the reference's ``np.random.randn(k) * 10``
+    per restart (bfgs.py:103).
+    """
+    y = y.squeeze()
+    Xt = torch.as_tensor(X)
+    if Xt.dim() == 2:
+        Xt = Xt.unsqueeze(0)
+    yt = torch.as_tensor(y).reshape(-1)
+    variables = list(test_data.total_variables)
+    R = int(_opt(cfg, "n_restarts"))
+
+    # ---- Q1-Q5 + compilation, per candidate (failures stay per candidate) ----
+    cands = []
+    for toks in pred_strs:
+        c = _Candidate()
+        try:
+            c.expr, c.k = skeleton_string(toks, cfg, test_data)
+            c.prog = compile_sympy(sp.sympify(c.expr), c.k, variables)
+        except Exception as exc:  # noqa: BLE001 -- the wrapper's contract (model.py:15-19)
+            c.error = exc
+        cands.append(c)
+    live = [i for i, c in enumerate(cands) if c.error is None]
+    results = [c.error for c in cands]
+    if not live:
+        return results
+
+    # ---- Q6 outlier rows ----
+    rows_removed = False
+    if _opt(cfg, "idx_remove", False):
+        keep = (Xt < 200).all(dim=2).squeeze(0)
+        rows_removed = bool((~keep).any())
+        Xt = Xt[:, keep, :]
+        yt_fit = yt[:Xt.shape[1]]  # the reference pairs kept rows with the first y's (bfgs.py:78-82)
+    else:
+        yt_fit = yt
+
+    # ---- Q7 normalisation ----
+    norm = _opt(cfg, "normalization_type")
+    if norm == "NMSE":
+        mean_y = float(yt_fit.double().mean())
+        scale = 1.0 / mean_y if abs(mean_y) > 1e-06 else 1.0
+    elif norm == "MSE":
+        scale = 1.0
+    else:
+        raise KeyError(norm)
+
+    eng = engine if engine is not None else fitter.get_engine(
+        Xt.device if Xt.is_cuda else None)
+    score_dtype = fitter.F32 if Xt.dtype == torch.float32 else fitter.F64
+    eval_dtype = fitter.F32 if str(_opt(cfg, "precision", "fp64")).lower() == "fp32" else fitter.F64
+    eng.set_points(Xt[0], yt_fit, dtypes=tuple({eval_dtype, score_dtype, fitter.F64}))
+    eng.set_programs([cands[i].prog for i in live])
+    opts = _engine_opts(cfg, scale, eval_dtype, score_dtype)
+
+    # ---- Q8 restarts: one run per (candidate, restart) ----
+    kmax = max(1, max(cands[i].k for i in live))
+    start = np.zeros((len(live) * R, kmax), dtype=np.float64)
+    run_prog, run_slot = [], []
+    for li, ci in enumerate(live):
+        k = cands[ci].k
+        for r in range(R):
+            if x0 is not None and x0[ci] is not None:
+                v = np.asarray(x0[ci], dtype=np.float64)[r][:k]
+            else:
+                v = np.random.randn(k) * 10
+            start[li * R + r, :k] = v
+            run_prog.append(li)
+            run_slot.append(li * R + r)
+    res = eng.fit(run_prog, run_slot, torch.from_numpy(start), opts)
+    lastx = res.lastx.cpu().numpy()
+    final = res.final_mse.cpu().numpy()
+    if score_dtype == fitter.F32:
+        final = final.astype(np.float32)
+    if rows_removed:
+        final = np.full_like(final, 1e9)  # y_found - y raises on the shape mismatch (bfgs.py:130-131)
+
+    # ---- Q10/Q11 pick the restart, Q12 collect prune work ----
+    thr = _opt(cfg, "prune_threshold", 1e-3)
+    tol = _opt(cfg, "prune_tolerance", 1.05)
+    picked = {}
+    prune_jobs = []
+    for li, ci in enumerate(live):
+        c = cands[ci]
+        F_loss = final[li * R:(li + 1) * R]
+        try:
+            k_best = int(np.nanargmin(F_loss))
+        except ValueError:
+            k_best = 0
+        best_consts = lastx[li * R + k_best, :c.k].copy()
+        best_loss = F_loss[k_best]
+        csyms = [sp.Symbol(f"c{i}") for i in range(c.k)]
+        picked[ci] = [best_consts, best_loss, csyms]
+        if c.k > 0:
+            zero_idx = []
+            for i, v in enumerate(best_consts):
+                if abs(v) < thr:
+                    if c.k == 1 and not sp.diff(c.expr, csyms[i]).is_constant():
+                        continue
+                    zero_idx.append(i)
+            if zero_idx:
+                rest = [i for i in range(c.k) if i not in zero_idx]
+                job = dict(ci=ci, zero=zero_idx, rest=rest, prog=None)
+                if rest:
+                    pruned = c.prog.expr.subs({csyms[i]: 0.0 for i in zero_idx})
+                    pruned = pruned.xreplace({csyms[i]: sp.Symbol(f"c{j}") for j, i in enumerate(rest)})
+                    try:
+                        job["prog"] = compile_sympy(pruned, len(rest), variables)
+                    except CompileError:
+                        job = None  # pruned loss cannot be evaluated: keep the unpruned fit
+                if job is not None:
+                    prune_jobs.append(job)
+
+    # ---- Q12 re-fit the pruned skeletons (one more BFGS each, from the best point) ----
+    fit_jobs = [j for j in prune_jobs if j["prog"] is not None]
+    if fit_jobs:
+        eng.set_programs([j["prog"] for j in fit_jobs])
+        pk = max(len(j["rest"]) for j in fit_jobs)
+        pstart = np.zeros((len(fit_jobs), pk), dtype=np.float64)
+        for ji, j in enumerate(fit_jobs):
+            pstart[ji, :len(j["rest"])] = picked[j["ci"]][0][j["rest"]]
+        pres = eng.fit(list(range(len(fit_jobs))), list(range(len(fit_jobs))),
+                       torch.from_numpy(pstart), opts)
+        # the reference scores res_pruned.x, not the last evaluated point (bfgs.py:180)
+        ploss, _ = eng.eval(list(range(len(fit_jobs))), pres.consts, dtype=score_dtype)
+        pconsts = pres.consts.cpu().numpy()
+        ploss = ploss.cpu().numpy()
+        for ji, j in enumerate(fit_jobs):
+            j["x"] = pconsts[ji, :len(j["rest"])]
+            j["loss"] = ploss[ji]
+    for j in prune_jobs:
+        c = cands[j["ci"]]
+        best_consts, best_loss, csyms = picked[j["ci"]]
+        vals = np.zeros(c.k)
+        if j["prog"] is not None:
+            vals[j["rest"]] = j["x"]
+            pruned_loss = j["loss"]
+        else:  # every constant pruned: evaluate the constant-free expression
+            zprog = compile_sympy(c.prog.expr.subs({s: 0.0 for s in csyms}), 0, variables)
+            eng.set_programs([zprog])
+            zl, _ = eng.eval([0], torch.zeros((1, 1)), dtype=score_dtype)
+            pruned_loss = float(zl.cpu().numpy()[0])
+        if score_dtype == fitter.F32:
+            pruned_loss = np.float32(pruned_loss)
+        if rows_removed:
+            pruned_loss = 1e9
+        ok = (pruned_loss < 1e-9) if best_loss == 0 else (pruned_loss <= best_loss * tol)
+        if ok:
+            picked[j["ci"]] = [vals, pruned_loss, csyms, True, j["zero"]]
+
+    # ---- Q13 strings ----
+    for ci in live:
+        c = cands[ci]
+        entry = picked[ci]
+        best_consts, best_loss, csyms = entry[0], entry[1], entry[2]
+        if c.k == 0:
+            results[ci] = (c.expr, [], best_loss, c.expr)
+            continue
+        if len(entry) > 3:  # pruned: zeros first, then the re-fitted ones (bfgs.py:184-196)
+            order = list(entry[4]) + [i for i in range(c.k) if i not in entry[4]]
+            vals = [0.0 if i in entry[4] else best_consts[i] for i in order]
+            final_expr = _substitute(c.expr, [csyms[i] for i in order], vals)
+            consts_out = [0.0 if i in entry[4] else best_consts[i] for i in range(c.k)]
+        else:
+            final_expr = _substitute(c.expr, csyms, list(best_consts))
+            consts_out = best_consts
+        results[ci] = (str(final_expr), consts_out, best_loss, c.expr)
+    return results
+
+
+def bfgs(pred_str, X, y, cfg, test_data, x0=None, engine=None):
+    """Reference signature (bfgs.py:42): one candidate, raises what the reference raises."""
+    out = bfgs_batch([pred_str], X, y, cfg, test_data,
+                     x0=None if x0 is None else [x0], engine=engine)[0]
+    if isinstance(out, Exception):
+        raise out
+    return out
