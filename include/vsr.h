@@ -126,6 +126,15 @@ int vsr_fit_host(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot
 /* Number of kernels this handle has launched since creation (bench.py reports it). */
 int64_t vsr_launch_count(const vsr_handle* h);
 
+/* Measurement hooks (bench.py): with profiling on, vsr_fit brackets its fit-kernel
+ * launches and its scoring launches with CUDA events on the caller's stream.
+ * vsr_read_profile synchronises on those events, returns the accumulated
+ *   out[0] fit-kernel milliseconds   out[1] number of fit-kernel launches
+ *   out[2] scoring milliseconds      out[3] number of scoring launches
+ * and resets the accumulators. */
+int vsr_set_profiling(vsr_handle* h, int32_t on);
+int vsr_read_profile(vsr_handle* h, double out[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,14 @@ struct vsr_handle {
   DevBuf d_stage;    // device staging of the *_host entry points
   PinnedBuf h_lists;
   int64_t launches = 0;
+  // measurement hooks
+  bool profiling = false;
+  struct Span {
+    cudaEvent_t a, b;
+    int kind, n;
+  };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
 };
 
 namespace {
@@ -112,6 +120,17 @@ int fail(vsr_handle* h, int code, const char* fmt, ...) {
   else
     g_create_error = buf;
   return code;
+}
+
+cudaEvent_t take_event(vsr_handle* h) {
+  if (!h->event_pool.empty()) {
+    cudaEvent_t e = h->event_pool.back();
+    h->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
 }
 
 #define VSR_CUDA(h, expr)                                                              \
@@ -334,12 +353,43 @@ void vsr_destroy(vsr_handle* h) {
   h->d_partial.release();
   h->d_stage.release();
   h->h_lists.release();
+  for (auto& sp : h->spans) {
+    if (sp.kind == 0) h->event_pool.push_back(sp.a);
+    h->event_pool.push_back(sp.b);
+  }
+  for (auto e : h->event_pool) cudaEventDestroy(e);
   delete h;
 }
 
 const char* vsr_last_error(const vsr_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int64_t vsr_launch_count(const vsr_handle* h) { return h ? h->launches : 0; }
+
+int vsr_set_profiling(vsr_handle* h, int32_t on) {
+  if (!h) return VSR_EINVAL;
+  h->profiling = on != 0;
+  return VSR_OK;
+}
+
+int vsr_read_profile(vsr_handle* h, double out[4]) {
+  if (!h || !out) return VSR_EINVAL;
+  out[0] = out[1] = out[2] = out[3] = 0.0;
+  // spans come in (fit, score) pairs sharing the middle event; ev_c closes the pair
+  for (size_t i = 0; i < h->spans.size(); ++i) {
+    auto& sp = h->spans[i];
+    VSR_CUDA(h, cudaEventSynchronize(sp.b));
+    float ms = 0.f;
+    VSR_CUDA(h, cudaEventElapsedTime(&ms, sp.a, sp.b));
+    out[sp.kind * 2] += ms;
+    out[sp.kind * 2 + 1] += sp.n;
+  }
+  for (size_t i = 0; i < h->spans.size(); ++i) {
+    if (h->spans[i].kind == 0) h->event_pool.push_back(h->spans[i].a);
+    h->event_pool.push_back(h->spans[i].b);
+  }
+  h->spans.clear();
+  return VSR_OK;
+}
 
 int vsr_set_points(vsr_handle* h, const void* X_dev, const void* y_dev, int64_t n_points,
                    int64_t ldx, int32_t n_vars, int32_t dtype) {
@@ -616,6 +666,13 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
   const int32_t* dl = (const int32_t*)h->d_lists.p;
 
   const PointSlot& ps = h->pts[opts->eval_dtype];
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+  if (h->profiling) {
+    ev_a = take_event(h);
+    ev_b = take_event(h);
+    ev_c = take_event(h);
+    VSR_CUDA(h, cudaEventRecord(ev_a, st));
+  }
   for (size_t gi = 0; gi < groups.size(); ++gi) {
     Group& g = groups[gi];
     const int n = (int)g.prog.size();
@@ -649,10 +706,16 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     if (e != cudaSuccess) return fail(h, VSR_ECUDA, "fit kernel launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
   }
+  if (h->profiling) VSR_CUDA(h, cudaEventRecord(ev_b, st));
   // per-restart score: plain MSE at the last evaluated point, in score_dtype (bfgs.py:120-132)
   rc = run_eval_group(h, 0, opts->score_dtype, dl + score_off, dl + score_off + n_runs,
                       dl + score_off + n_runs, n_runs, s_kmax, s_insn, s_imm, out_lastx, kstride,
                       out_final_mse, nullptr, st);
+  if (h->profiling) {
+    VSR_CUDA(h, cudaEventRecord(ev_c, st));
+    h->spans.push_back({ev_a, ev_b, 0, (int)groups.size()});
+    h->spans.push_back({ev_b, ev_c, 1, 2});
+  }
   return rc;
 }
 

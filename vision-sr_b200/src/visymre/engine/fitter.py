@@ -88,6 +88,15 @@ class Engine:
     def launches(self):
         return int(self.lib.vsr_launch_count(self._h))
 
+    def set_profiling(self, on):
+        self._check(self.lib.vsr_set_profiling(self._h, int(bool(on))))
+
+    def read_profile(self):
+        """(fit_ms, fit_launches, score_ms, score_launches) since the last read."""
+        out = (ctypes.c_double * 4)()
+        self._check(self.lib.vsr_read_profile(self._h, out))
+        return tuple(out)
+
     # ---- points ----------------------------------------------------------------------
     def set_points(self, X, y, dtypes=(F64,), n_vars=None):
         """X: [N, d] (or [1, N, d]) tensor/array on any device; y: squeezable to [N].

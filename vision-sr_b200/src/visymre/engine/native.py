@@ -53,6 +53,8 @@ SIGNATURES = {
                                     ctypes.c_int32, ctypes.POINTER(FitOpts), vp, vp, vp, vp, vp,
                                     vp]),
     "vsr_launch_count": (ctypes.c_int64, [vp]),
+    "vsr_set_profiling": (ctypes.c_int, [vp, ctypes.c_int32]),
+    "vsr_read_profile": (ctypes.c_int, [vp, c_f64p]),
 }
 
 _lib = None
