@@ -133,6 +133,10 @@ int64_t vsr_launch_count(const vsr_handle* h);
  *   out[2] scoring milliseconds      out[3] number of scoring launches
  * and resets the accumulators. */
 int vsr_set_profiling(vsr_handle* h, int32_t on);
+/* Optional: a device int64 buffer [n_slots][8]; the fit kernel then records, per run, the
+ * SM cycles its leader thread spent in each phase of the pass loop (optimiser logic,
+ * barriers, sweep, reductions) and the number of passes.  NULL switches it off. */
+int vsr_set_phase_buffer(vsr_handle* h, void* dev_i64_nslots_by_8);
 int vsr_read_profile(vsr_handle* h, double out[4]);
 
 #ifdef __cplusplus

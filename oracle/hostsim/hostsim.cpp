@@ -43,7 +43,7 @@ void sweep(const vsr_insn_t* prog, const double* imm, const double* c, int k, co
     s += r * r;
     for (int t = 0; t < K; ++t) {
       const double gt = 2.0 * r * (double)acc[0].d[t];
-      g[t] += (r == r && std::isfinite(r) && !std::isfinite(gt)) ? 0.0 : gt;
+      g[t] += std::isfinite(gt) ? gt : 0.0;
     }
   }
   *out_sum = s;
@@ -61,6 +61,15 @@ int sweep_dispatch(int K, const vsr_insn_t* prog, const double* imm, const doubl
   return -1;
 }
 
+std::vector<vsr_insn_t> predecoded(const vsr_insn_t* prog) {
+  std::vector<vsr_insn_t> out;
+  for (int i = 0;; ++i) {
+    out.push_back(vsr::predecode(prog[i]));
+    if (VSR_OP(prog[i]) == VSR_END) break;
+  }
+  return out;
+}
+
 int pick_K(int k) {
   static const int ks[] = {0, 1, 2, 3, 4, 6, 8, 12, 16};
   for (int v : ks)
@@ -73,8 +82,10 @@ int pick_K(int k) {
 extern "C" {
 
 // values f(x_i; c) for every point (K = 0), for interpreter-vs-lambdify tests
-int hostsim_values(const vsr_insn_t* prog, const double* imm, const double* c, int k,
+int hostsim_values(const vsr_insn_t* raw_prog, const double* imm, const double* c, int k,
                    const void* X, long N, int dtype, double* out) {
+  const std::vector<vsr_insn_t> pd = predecoded(raw_prog);
+  const vsr_insn_t* prog = pd.data();
   if (dtype == VSR_F64) {
     const double* Xd = (const double*)X;
     double cst[VSR_MAX_CONSTS];
@@ -104,9 +115,11 @@ int hostsim_values(const vsr_insn_t* prog, const double* imm, const double* c, i
 }
 
 // mean squared residual and its gradient w.r.t. the constants (dual numbers)
-int hostsim_loss_grad(const vsr_insn_t* prog, const double* imm, const double* c, int k,
+int hostsim_loss_grad(const vsr_insn_t* raw_prog, const double* imm, const double* c, int k,
                       const void* X, const void* y, long N, int dtype, int want_grad,
                       double* out_loss, double* out_grad) {
+  const std::vector<vsr_insn_t> pd = predecoded(raw_prog);
+  const vsr_insn_t* prog = pd.data();
   const int K = want_grad ? pick_K(k) : 0;
   if (K < 0) return -1;
   double s = 0.0, g[VSR_MAX_DUAL] = {0};
@@ -123,10 +136,12 @@ int hostsim_loss_grad(const vsr_insn_t* prog, const double* imm, const double* c
 }
 
 // one BFGS run driven by the same state machine the fit kernel runs
-int hostsim_fit(const vsr_insn_t* prog, const double* imm, int k, const void* X, const void* y,
+int hostsim_fit(const vsr_insn_t* raw_prog, const double* imm, int k, const void* X, const void* y,
                 long N, int dtype, const double* x0, int grad_mode, double loss_scale,
                 double gtol, int maxiter_per_k, double* out_x, double* out_lastx,
                 double* out_fun, int* out_status, int* out_nit, int* out_nfev) {
+  const std::vector<vsr_insn_t> pd = predecoded(raw_prog);
+  const vsr_insn_t* prog = pd.data();
   vsr::FitOpts O;
   O.gtol = gtol;
   O.c1 = 1e-4;

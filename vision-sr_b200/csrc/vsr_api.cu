@@ -89,7 +89,10 @@ struct vsr_handle {
   PointSlot pts[2];
   // programs
   DevBuf d_insns, d_insn_off, d_imms, d_imm_off, d_k;
-  std::vector<int32_t> h_k, h_ninsn, h_nimm;
+  std::vector<int32_t> h_k, h_ninsn, h_nimm, h_nvars;
+  std::vector<cudaStream_t> side_streams;
+  cudaEvent_t ev_fork = nullptr;
+  std::vector<cudaEvent_t> ev_join;
   int n_programs = 0;
   // scratch
   DevBuf d_lists;    // grouped run / pair lists
@@ -99,6 +102,7 @@ struct vsr_handle {
   int64_t launches = 0;
   // measurement hooks
   bool profiling = false;
+  long long* phase_cycles = nullptr;  // optional device buffer [n_slots][8], see vsr_set_phase_buffer
   struct Span {
     cudaEvent_t a, b;
     int kind, n;
@@ -161,28 +165,52 @@ vsr::Points points_of(const PointSlot& s) {
 }
 
 // points per thread for a tangent width: wide duals are register hungry
-constexpr int points_per_thread(int K) { return K <= 4 ? 2 : 1; }
+constexpr int points_per_thread(int K) { return K <= 8 ? 2 : 1; }
 
 template <typename T, int K>
-cudaError_t launch_fit_T(const vsr::FitArgs& a, int threads, size_t smem, cudaStream_t st) {
+cudaError_t launch_fit_T(const vsr::FitArgs& a, int threads, int cs, size_t smem, cudaStream_t st) {
   constexpr int P = points_per_thread(K);
   auto kern = vsr::fit_kernel<T, K, P>;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (threads > vsr::fit_max_threads<T, K>()) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
+  if (e != cudaSuccess) return e;
+  if (cs > 8) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return e;
   }
-  kern<<<a.n_runs, threads, smem, st>>>(a);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)a.n_runs * cs);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 template <typename T>
-cudaError_t launch_fit(int K, const vsr::FitArgs& a, int threads, size_t smem, cudaStream_t st) {
+cudaError_t launch_fit(int K, const vsr::FitArgs& a, int threads, int cs, size_t smem, cudaStream_t st) {
   switch (K) {
-#define C(KK) case KK: return launch_fit_T<T, KK>(a, threads, smem, st);
+#define C(KK) case KK: return launch_fit_T<T, KK>(a, threads, cs, smem, st);
     C(0) C(1) C(2) C(3) C(4) C(6) C(8) C(12) C(16)
 #undef C
   }
   return cudaErrorInvalidValue;
+}
+
+template <typename T>
+int fit_threads_cap(int K) {
+  switch (K) {
+#define C(KK) case KK: return vsr::fit_max_threads<T, KK>();
+    C(0) C(1) C(2) C(3) C(4) C(6) C(8) C(12) C(16)
+#undef C
+  }
+  return 256;
 }
 
 template <typename T, int K>
@@ -210,20 +238,43 @@ int next_pow2(int64_t v) {
   return p;
 }
 
-// warps per run: enough lanes that a sweep is a handful of tile iterations, more when
-// there are too few runs to fill 148 SMs
-int choose_warps(const vsr_handle* h, int64_t N, int n_runs, int P, int forced) {
-  if (forced > 0) return std::min(8, std::max(1, forced));
-  int w = std::min<int64_t>(8, std::max<int64_t>(1, next_pow2((N + 32 * P * 4 - 1) / (32 * P * 4))));
-  while (w < 8 && (int64_t)n_runs * w < (int64_t)h->num_sms * 16 && N / (32 * P * w) >= 2) w <<= 1;
-  return w;
+// Geometry of one run: a cluster of `cs` CTAs of `threads` threads, each CTA owning a
+// contiguous slice of `stride` points.  Aim: a pass over the points is one or two tile
+// iterations per thread (the optimiser's critical path is passes x latency per pass), and
+// the slice fits the CTA's shared memory so the points are read from HBM once per run.
+struct Geometry {
+  int cs, threads, stride, resident;
+  size_t smem;
+};
+
+constexpr int kMaxCluster = 16;              // 16 needs the non-portable cluster size opt-in
+constexpr size_t kSmemBudget = 200 * 1024;  // of the 227 KB a CTA can own; leaves room for static smem
+
+Geometry choose_geometry(int64_t N, int P, int cap_threads, int forced_warps, int kmax, int K, int max_insn,
+                         int max_imm, int max_slots, int elem) {
+  Geometry g;
+  const int64_t per_iter = (int64_t)cap_threads * P;
+  int cs = 1;
+  while (cs < kMaxCluster && (N + cs - 1) / cs > per_iter) cs <<= 1;
+  int64_t per = (N + cs - 1) / cs;
+  per = (per + 31) & ~(int64_t)31;
+  int threads = (int)std::min<int64_t>(cap_threads, ((per + P - 1) / P + 31) & ~(int64_t)31);
+  if (forced_warps > 0) threads = std::min(cap_threads, 32 * forced_warps);
+  threads = std::max(32, threads);
+  g.cs = cs;
+  g.threads = threads;
+  g.stride = (int)per;
+  const size_t with = vsr::fit_smem_bytes(kmax, K, threads / 32, cs, max_insn, max_imm, max_slots, (int)per, elem);
+  g.resident = with <= kSmemBudget && per < (1 << 30);
+  g.smem = g.resident ? with : vsr::fit_smem_bytes(kmax, K, threads / 32, cs, max_insn, max_imm, -1, 0, elem);
+  return g;
 }
 
 struct Group {
   int K;
   int grad_mode;
   std::vector<int32_t> prog, slot;
-  int kmax = 0, max_insn = 0, max_imm = 0;
+  int kmax = 0, max_insn = 0, max_imm = 0, max_slots = 0;
 };
 
 // copies host int32 lists into the handle's device list buffer at `offset` (in ints)
@@ -353,6 +404,9 @@ void vsr_destroy(vsr_handle* h) {
   h->d_partial.release();
   h->d_stage.release();
   h->h_lists.release();
+  for (auto s2 : h->side_streams) cudaStreamDestroy(s2);
+  for (auto e2 : h->ev_join) cudaEventDestroy(e2);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (auto& sp : h->spans) {
     if (sp.kind == 0) h->event_pool.push_back(sp.a);
     h->event_pool.push_back(sp.b);
@@ -364,6 +418,12 @@ void vsr_destroy(vsr_handle* h) {
 const char* vsr_last_error(const vsr_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int64_t vsr_launch_count(const vsr_handle* h) { return h ? h->launches : 0; }
+
+int vsr_set_phase_buffer(vsr_handle* h, void* dev_i64_nslots_by_8) {
+  if (!h) return VSR_EINVAL;
+  h->phase_cycles = (long long*)dev_i64_nslots_by_8;
+  return VSR_OK;
+}
 
 int vsr_set_profiling(vsr_handle* h, int32_t on) {
   if (!h) return VSR_EINVAL;
@@ -445,6 +505,7 @@ int vsr_upload_programs(vsr_handle* h, const uint64_t* insns, const int32_t* ins
   h->h_k.assign(k, k + n_programs);
   h->h_ninsn.resize(n_programs);
   h->h_nimm.resize(n_programs);
+  h->h_nvars.assign(n_programs, 0);
   for (int c = 0; c < n_programs; ++c) {
     const int ni = insn_off[c + 1] - insn_off[c];
     const int nm = imm_off[c + 1] - imm_off[c];
@@ -454,6 +515,7 @@ int vsr_upload_programs(vsr_handle* h, const uint64_t* insns, const int32_t* ins
       return fail(h, VSR_EINVAL, "program %d does not end in END", c);
     // static check of operand indices and stack discipline: the kernels trust the table
     int sp = 0;
+    unsigned var_mask = 0;
     for (int i = insn_off[c]; i < insn_off[c + 1]; ++i) {
       const unsigned op = VSR_OP(insns[i]), src = VSR_SRC(insns[i]), idx = VSR_IDX(insns[i]);
       if (op >= VSR_OP_COUNT) return fail(h, VSR_EINVAL, "program %d: bad opcode %u", c, op);
@@ -463,6 +525,7 @@ int vsr_upload_programs(vsr_handle* h, const uint64_t* insns, const int32_t* ins
           if (--sp < 0) return fail(h, VSR_EINVAL, "program %d: stack underflow", c);
         } else if (src == VSR_SRC_VAR) {
           if (idx >= VSR_MAX_VARS) return fail(h, VSR_EINVAL, "program %d: variable %u", c, idx);
+          var_mask |= 1u << idx;
         } else if (src == VSR_SRC_CONST) {
           if ((int)idx >= k[c]) return fail(h, VSR_EINVAL, "program %d: constant %u of %d", c, idx, k[c]);
         } else if (src == VSR_SRC_IMM) {
@@ -474,6 +537,7 @@ int vsr_upload_programs(vsr_handle* h, const uint64_t* insns, const int32_t* ins
     }
     h->h_ninsn[c] = ni;
     h->h_nimm[c] = nm;
+    h->h_nvars[c] = __builtin_popcount(var_mask);
   }
   const size_t nins = insn_off[n_programs], nimm = std::max(1, imm_off[n_programs]);
   VSR_CUDA(h, h->d_insns.reserve(nins * sizeof(uint64_t)));
@@ -627,13 +691,19 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     g.kmax = std::max(g.kmax, k);
     g.max_insn = std::max(g.max_insn, h->h_ninsn[c]);
     g.max_imm = std::max(g.max_imm, h->h_nimm[c]);
+    g.max_slots = std::max(g.max_slots, h->h_nvars[c]);
   }
-  // longest programs first inside a group so the tail of the launch is short runs
+  // widest groups first: their runs have the highest iteration caps (200 k)
+  std::stable_sort(groups.begin(), groups.end(), [](const Group& x, const Group& y) { return x.kmax > y.kmax; });
+  // potentially longest runs first (iteration cap is 200 k, cost per pass grows with the
+  // program) so the tail of the launch is short runs
   for (auto& g : groups) {
     std::vector<int> order(g.prog.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-      return h->h_ninsn[g.prog[a]] * (1 + h->h_k[g.prog[a]]) > h->h_ninsn[g.prog[b]] * (1 + h->h_k[g.prog[b]]);
+      const int ka = h->h_k[g.prog[a]], kb = h->h_k[g.prog[b]];
+      if (ka != kb) return ka > kb;
+      return h->h_ninsn[g.prog[a]] > h->h_ninsn[g.prog[b]];
     });
     std::vector<int32_t> p2(order.size()), s2(order.size());
     for (size_t i = 0; i < order.size(); ++i) {
@@ -666,6 +736,8 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
   const int32_t* dl = (const int32_t*)h->d_lists.p;
 
   const PointSlot& ps = h->pts[opts->eval_dtype];
+  const int elem = opts->eval_dtype == VSR_F64 ? 8 : 4;
+  const bool tma_ok = ((uintptr_t)ps.X % 16 == 0) && ((uintptr_t)ps.y % 16 == 0) && ((ps.ldx * elem) % 16 == 0);
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
   if (h->profiling) {
     ev_a = take_event(h);
@@ -673,9 +745,26 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     ev_c = take_event(h);
     VSR_CUDA(h, cudaEventRecord(ev_a, st));
   }
+  // groups run concurrently: group 0 on the caller's stream, the others on side streams
+  // forked from / joined to it with events
+  const size_t n_side = groups.size() > 1 ? groups.size() - 1 : 0;
+  while (h->side_streams.size() < n_side) {
+    cudaStream_t s2;
+    VSR_CUDA(h, cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    h->side_streams.push_back(s2);
+    cudaEvent_t e2;
+    VSR_CUDA(h, cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    h->ev_join.push_back(e2);
+  }
+  if (n_side) {
+    if (!h->ev_fork) VSR_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    VSR_CUDA(h, cudaEventRecord(h->ev_fork, st));
+  }
   for (size_t gi = 0; gi < groups.size(); ++gi) {
     Group& g = groups[gi];
     const int n = (int)g.prog.size();
+    cudaStream_t gs = gi == 0 ? st : h->side_streams[gi - 1];
+    if (gi > 0) VSR_CUDA(h, cudaStreamWaitEvent(gs, h->ev_fork, 0));
     vsr::FitArgs a;
     a.pt = table_of(h);
     a.pts = points_of(ps);
@@ -699,12 +788,23 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     a.O.maxiter_per_k = opts->maxiter_per_k;
     a.O.grad_mode = g.grad_mode;
     const int P = points_per_thread(g.K);
-    const int warps = g.kmax == 0 ? 1 : choose_warps(h, ps.n, n, P, opts->warps_per_run);
-    const size_t smem = sizeof(double) * (size_t)vsr::fit_smem_doubles(g.kmax, g.K, warps, g.max_insn, g.max_imm);
-    cudaError_t e = opts->eval_dtype == VSR_F64 ? launch_fit<double>(g.K, a, warps * 32, smem, st)
-                                                : launch_fit<float>(g.K, a, warps * 32, smem, st);
-    if (e != cudaSuccess) return fail(h, VSR_ECUDA, "fit kernel launch failed: %s", cudaGetErrorString(e));
+    const int cap = opts->eval_dtype == VSR_F64 ? fit_threads_cap<double>(g.K) : fit_threads_cap<float>(g.K);
+    Geometry geo = choose_geometry(g.kmax == 0 ? 1 : ps.n, P, cap, opts->warps_per_run, g.kmax, g.K,
+                                   g.max_insn, g.max_imm, g.max_slots, elem);
+    a.phase_cycles = h->phase_cycles;
+    a.resident = geo.resident;
+    a.tma_ok = tma_ok ? 1 : 0;
+    a.slice_stride = geo.stride;
+    cudaError_t e = opts->eval_dtype == VSR_F64 ? launch_fit<double>(g.K, a, geo.threads, geo.cs, geo.smem, gs)
+                                                : launch_fit<float>(g.K, a, geo.threads, geo.cs, geo.smem, gs);
+    if (e != cudaSuccess)
+      return fail(h, VSR_ECUDA, "fit kernel launch failed (K=%d threads=%d cluster=%d smem=%zu): %s", g.K,
+                  geo.threads, geo.cs, geo.smem, cudaGetErrorString(e));
     h->launches += 1;
+    if (gi > 0) {
+      VSR_CUDA(h, cudaEventRecord(h->ev_join[gi - 1], gs));
+      VSR_CUDA(h, cudaStreamWaitEvent(st, h->ev_join[gi - 1], 0));
+    }
   }
   if (h->profiling) VSR_CUDA(h, cudaEventRecord(ev_b, st));
   // per-restart score: plain MSE at the last evaluated point, in score_dtype (bfgs.py:120-132)

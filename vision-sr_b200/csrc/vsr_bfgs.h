@@ -13,13 +13,21 @@
 //   ScalarFunction caching      scipy/optimize/_differentiable_functions.py:128-420
 //   '2-point' forward difference scipy/optimize/_numdiff.py:580-700
 //
-// Why a state machine: on the GPU one CTA owns one (candidate, restart) run.  Thread 0
-// advances the optimiser until it needs the objective at a new point, then returns
-// VSR_NEED_EVAL; ALL threads of the CTA then sweep the data points together (they
-// reach the sweep convergently, so warp shuffles and __syncthreads are legal), and
-// thread 0 resumes.  scipy's nested calls (BFGS -> line search -> phi/derphi ->
+// Why a state machine: on the GPU one cluster owns one (candidate, restart) run.  WARP 0
+// of the leader CTA advances the optimiser until it needs the objective at a new point,
+// then returns VSR_NEED_EVAL; ALL threads of the cluster then sweep the data points
+// together (they reach the sweep convergently, so warp shuffles and barriers are legal),
+// and warp 0 resumes.  scipy's nested calls (BFGS -> line search -> phi/derphi ->
 // ScalarFunction) are flattened into one protothread-style function; every variable
 // that lives across an evaluation is a member of FitState.
+//
+// Execution model of fit_step on the device (a single GPU thread is ~30x slower than a
+// CPU core on serial code, so the linear algebra must not be serial): all 32 lanes of the
+// warp run the SAME control flow on identical scalar values -- each lane owns a private
+// FitState -- while the length-k vectors live in shared memory with element i handled by
+// lane i: O(k) loops take one step, O(k^2) ones (H g, the BFGS update) k steps, dot
+// products are warp-shuffle sums.  On the host `Lanes` degenerates to one lane and the
+// loops are ordinary loops.
 //
 // The same header is compiled by g++ into oracle/hostsim (CPU tests check the logic
 // against scipy itself); the product path only runs the CUDA build.
@@ -51,6 +59,40 @@ struct FitOpts {
 };
 
 enum { VSR_NEED_EVAL = 1, VSR_DONE = 0 };
+
+// lane context of fit_step / fit_init
+struct Lanes {
+#if defined(__CUDA_ARCH__)
+  static __device__ __forceinline__ int first() { return (int)(threadIdx.x & 31u); }
+  static __device__ __forceinline__ int step() { return 32; }
+  static __device__ __forceinline__ void sync() { __syncwarp(); }
+  static __device__ __forceinline__ double sum(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+  }
+  static __device__ __forceinline__ double maxv(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      const double o = __shfl_xor_sync(0xffffffffu, v, m);
+      v = o > v ? o : v;
+    }
+    return v;
+  }
+  static __device__ __forceinline__ bool any(bool b) { return __any_sync(0xffffffffu, b) != 0; }
+  static __device__ __forceinline__ bool all(bool b) { return __all_sync(0xffffffffu, b) != 0; }
+#else
+  static int first() { return 0; }
+  static int step() { return 1; }
+  static void sync() {}
+  static double sum(double v) { return v; }
+  static double maxv(double v) { return v; }
+  static bool any(bool b) { return b; }
+  static bool all(bool b) { return b; }
+#endif
+};
+// element i of a length-k vector is handled by lane i (all of them by the host's one lane)
+#define VSR_FOR_K(i, k) for (int i = Lanes::first(); i < (k); i += Lanes::step())
 
 // DCSRCH task codes
 enum { DC_START = 0, DC_FG = 1, DC_CONV = 2, DC_WARN = 3, DC_ERROR = 4 };
@@ -114,7 +156,7 @@ VSR_HDN inline void fit_init(FitState& S, int k, double* ws, const double* x0) {
   S.gnew = ws + 9 * k;
   S.Hy = ws + 10 * k;
   S.H = ws + 11 * k;
-  for (int i = 0; i < k; ++i) {
+  VSR_FOR_K(i, k) {
     S.xk[i] = x0[i];
     S.lastx[i] = x0[i];
   }
@@ -362,34 +404,35 @@ VSR_HDN inline bool quadmin(double a, double fa, double fpa, double b, double fb
 #define VSR_CO_YIELD(S) VSR_CO_YIELD_(S, __COUNTER__)
 
 // ScalarFunction._update_x via fun()/grad(): np.array_equal(x, self.x)
-#define VSR_OBJ_SETX(S, xptr)                          \
-  do {                                                 \
-    int same_ = 1;                                     \
-    for (int i_ = 0; i_ < (S).k; ++i_)                 \
-      if (!((xptr)[i_] == (S).cx[i_])) same_ = 0;      \
-    if (!same_) {                                      \
-      for (int i_ = 0; i_ < (S).k; ++i_) (S).cx[i_] = (xptr)[i_]; \
-      (S).f_ok = 0;                                    \
-      (S).g_ok = 0;                                    \
-    }                                                  \
+#define VSR_OBJ_SETX(S, xptr)                                      \
+  do {                                                             \
+    bool same_ = true;                                             \
+    VSR_FOR_K(i_, (S).k)                                           \
+    if (!((xptr)[i_] == (S).cx[i_])) same_ = false;                \
+    same_ = Lanes::all(same_);                                     \
+    if (!same_) {                                                  \
+      VSR_FOR_K(i_, (S).k)(S).cx[i_] = (xptr)[i_];                 \
+      (S).f_ok = 0;                                                \
+      (S).g_ok = 0;                                                \
+    }                                                              \
   } while (0)
 
 // ScalarFunction._update_fun.  In dual mode one sweep returns f and its gradient.
-#define VSR_OBJ_UPDATE_FUN(S, O)                                         \
-  do {                                                                   \
-    if (!(S).f_ok) {                                                     \
-      for (int i_ = 0; i_ < (S).k; ++i_) (S).xe[i_] = (S).cx[i_];        \
-      VSR_CO_YIELD(S);                                                   \
-      (S).cf = (S).rf;                                                   \
-      (S).nfev += 1;                                                     \
-      (S).f_ok = 1;                                                      \
-      for (int i_ = 0; i_ < (S).k; ++i_) (S).lastx[i_] = (S).xe[i_];     \
-      if ((O).grad_mode == VSR_GRAD_DUAL) {                              \
-        for (int i_ = 0; i_ < (S).k; ++i_) (S).cg[i_] = (S).rg[i_];      \
-        (S).g_ok = 1;                                                    \
-        (S).ngev += 1;                                                   \
-      }                                                                  \
-    }                                                                    \
+#define VSR_OBJ_UPDATE_FUN(S, O)                                   \
+  do {                                                             \
+    if (!(S).f_ok) {                                               \
+      VSR_FOR_K(i_, (S).k)(S).xe[i_] = (S).cx[i_];                 \
+      VSR_CO_YIELD(S);                                             \
+      (S).cf = (S).rf;                                             \
+      (S).nfev += 1;                                               \
+      (S).f_ok = 1;                                                \
+      VSR_FOR_K(i_, (S).k)(S).lastx[i_] = (S).xe[i_];              \
+      if ((O).grad_mode == VSR_GRAD_DUAL) {                        \
+        VSR_FOR_K(i_, (S).k)(S).cg[i_] = (S).rg[i_];               \
+        (S).g_ok = 1;                                              \
+        (S).ngev += 1;                                             \
+      }                                                            \
+    }                                                              \
   } while (0)
 
 // ScalarFunction._update_grad; FD branch = approx_derivative('2-point', abs_step=eps)
@@ -400,6 +443,7 @@ VSR_HDN inline bool quadmin(double a, double fa, double fpa, double b, double fb
       if (!(S).g_ok) {                                                               \
         for ((S).fd_i = 0; (S).fd_i < (S).k; ++(S).fd_i) {                           \
           {                                                                          \
+            Lanes::sync(); /* cx[fd_i] was written by its owner lane */              \
             const double x_ = (S).cx[(S).fd_i];                                      \
             double h_ = (O).fd_eps;                                                  \
             if ((x_ + h_) - x_ == 0.0) {                                             \
@@ -407,13 +451,14 @@ VSR_HDN inline bool quadmin(double a, double fa, double fpa, double b, double fb
               h_ = 1.4901161193847656e-08 * (x_ >= 0 ? 1.0 : -1.0) * a_;             \
             }                                                                        \
             (S).fd_dx = (x_ + h_) - x_;                                              \
-            for (int i_ = 0; i_ < (S).k; ++i_) (S).xe[i_] = (S).cx[i_];              \
-            (S).xe[(S).fd_i] = x_ + h_;                                              \
+            VSR_FOR_K(i_, (S).k)(S).xe[i_] = (i_ == (S).fd_i) ? x_ + h_ : (S).cx[i_]; \
           }                                                                          \
           VSR_CO_YIELD(S);                                                           \
-          (S).cg[(S).fd_i] = ((S).rf - (S).cf) / (S).fd_dx;                          \
+          VSR_FOR_K(i_, (S).k) {                                                     \
+            if (i_ == (S).fd_i) (S).cg[i_] = ((S).rf - (S).cf) / (S).fd_dx;          \
+            (S).lastx[i_] = (S).xe[i_];                                              \
+          }                                                                          \
           (S).nfev += 1;                                                             \
-          for (int i_ = 0; i_ < (S).k; ++i_) (S).lastx[i_] = (S).xe[i_];             \
         }                                                                            \
         (S).g_ok = 1;                                                                \
         (S).ngev += 1;                                                               \
@@ -426,24 +471,24 @@ VSR_HDN inline bool quadmin(double a, double fa, double fpa, double b, double fb
 // uses so the ScalarFunction cache hits exactly when scipy's does.
 #define VSR_LS_PHI(S, O, a, out)                                                  \
   do {                                                                            \
-    for (int i_ = 0; i_ < (S).k; ++i_) (S).xt[i_] = (S).xk[i_] + (a) * (S).pk[i_]; \
+    VSR_FOR_K(i_, (S).k)(S).xt[i_] = (S).xk[i_] + (a) * (S).pk[i_];               \
     VSR_OBJ_SETX(S, (S).xt);                                                      \
     VSR_OBJ_UPDATE_FUN(S, O);                                                     \
     (out) = (S).cf;                                                               \
   } while (0)
 #define VSR_LS_DERPHI(S, O, a, out)                                               \
   do {                                                                            \
-    for (int i_ = 0; i_ < (S).k; ++i_) (S).xt[i_] = (S).xk[i_] + (a) * (S).pk[i_]; \
+    VSR_FOR_K(i_, (S).k)(S).xt[i_] = (S).xk[i_] + (a) * (S).pk[i_];               \
     VSR_OBJ_SETX(S, (S).xt);                                                      \
     VSR_OBJ_UPDATE_GRAD(S, O);                                                    \
     {                                                                             \
       double d_ = 0.0;                                                            \
-      for (int i_ = 0; i_ < (S).k; ++i_) {                                        \
+      VSR_FOR_K(i_, (S).k) {                                                      \
         (S).gnew[i_] = (S).cg[i_];                                                \
         d_ += (S).cg[i_] * (S).pk[i_];                                            \
       }                                                                           \
       (S).have_gnew = 1;                                                          \
-      (out) = d_;                                                                 \
+      (out) = Lanes::sum(d_);                                                     \
     }                                                                             \
   } while (0)
 
@@ -456,42 +501,46 @@ VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
   switch (S.pc) {
     case 0:
       // ScalarFunction.__init__: f and grad at x0
-      for (int i = 0; i < k; ++i) S.cx[i] = S.xk[i];
+      VSR_FOR_K(i, k) S.cx[i] = S.xk[i];
       S.f_ok = S.g_ok = 0;
       VSR_OBJ_UPDATE_FUN(S, O);
       VSR_OBJ_UPDATE_GRAD(S, O);
       S.old_fval = S.cf;
-      for (int i = 0; i < k; ++i) S.gfk[i] = S.cg[i];
       S.it = 0;
       S.maxiter = k * O.maxiter_per_k;
-      for (int i = 0; i < k * k; ++i) S.H[i] = 0.0;
-      for (int i = 0; i < k; ++i) S.H[i * k + i] = 1.0;
       {
         double n2 = 0.0, gm = 0.0;
         bool gnan = false;
-        for (int i = 0; i < k; ++i) {
-          n2 += S.gfk[i] * S.gfk[i];
-          if (nan_d(S.gfk[i])) gnan = true;
-          if (abs_d(S.gfk[i]) > gm) gm = abs_d(S.gfk[i]);
+        VSR_FOR_K(i, k) {
+          const double gi = S.cg[i];
+          S.gfk[i] = gi;
+          for (int j = 0; j < k; ++j) S.H[i * k + j] = (i == j) ? 1.0 : 0.0;
+          n2 += gi * gi;
+          if (nan_d(gi)) gnan = true;
+          if (abs_d(gi) > gm) gm = abs_d(gi);
         }
+        n2 = Lanes::sum(n2);
+        gm = Lanes::maxv(gm);
+        gnan = Lanes::any(gnan);
         S.old_old_fval = S.old_fval + ::sqrt(n2) / 2;
         S.gnorm = gnan ? ::nan("") : gm;  // vecnorm(gfk, inf) = amax(|gfk|), nan propagates
       }
       S.warnflag = 0;
 
       while (S.gnorm > O.gtol && S.it < S.maxiter) {
-        // pk = -Hk . gfk
-        for (int i = 0; i < k; ++i) {
-          double acc = 0.0;
-          for (int j = 0; j < k; ++j) acc += S.H[i * k + j] * S.gfk[j];
-          S.pk[i] = -acc;
-        }
-        // ---------------- line_search_wolfe1 ----------------
+        // pk = -Hk . gfk   (row i on lane i)
+        Lanes::sync();
         {
           double d = 0.0;
-          for (int i = 0; i < k; ++i) d += S.gfk[i] * S.pk[i];
-          S.derphi0 = d;
+          VSR_FOR_K(i, k) {
+            double acc = 0.0;
+            for (int j = 0; j < k; ++j) acc += S.H[i * k + j] * S.gfk[j];
+            S.pk[i] = -acc;
+            d += S.gfk[i] * -acc;
+          }
+          S.derphi0 = Lanes::sum(d);
         }
+        // ---------------- line_search_wolfe1 ----------------
         S.phi0 = S.old_fval;
         S.old_phi0 = S.old_old_fval;
         S.have_gnew = 0;  // gval = [gfk]
@@ -528,8 +577,7 @@ VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
           S.ls_fval = S.phi1;
           S.ls_oldfval = S.phi0;
           // gval[0]: gradient of the last derphi call (gfk when there was none)
-          if (!S.have_gnew)
-            for (int i = 0; i < k; ++i) S.gnew[i] = S.gfk[i];
+          if (!S.have_gnew) VSR_FOR_K(i, k) S.gnew[i] = S.gfk[i];
           S.have_gnew = 1;
         } else {
           // ---------------- line_search_wolfe2 (fallback) ----------------
@@ -681,30 +729,34 @@ VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
         VSR_TRACE(S);
 #endif
         // xkp1 = xk + alpha_k*pk
-        for (int i = 0; i < k; ++i) {
+        VSR_FOR_K(i, k) {
           S.Hy[i] = S.alpha_k * S.pk[i];  // sk (kept in Hy until the update below)
           S.xt[i] = S.xk[i] + S.Hy[i];
         }
         if (!S.have_gnew) {
           VSR_OBJ_SETX(S, S.xt);
           VSR_OBJ_UPDATE_GRAD(S, O);
-          for (int i = 0; i < k; ++i) S.gnew[i] = S.cg[i];
-          // sk was clobbered? no: Hy is untouched by the objective macros
+          VSR_FOR_K(i, k) S.gnew[i] = S.cg[i];
         }
         {
-          // yk = gfkp1 - gfk (stored in gfk's old slot via pk: pk is free now)
-          double gm = 0.0;
+          double gm = 0.0, pn2 = 0.0, xn2 = 0.0, ys = 0.0;
           bool gnan = false;
-          double pn2 = 0.0, xn2 = 0.0;
-          for (int i = 0; i < k; ++i) {
+          VSR_FOR_K(i, k) {
             pn2 += S.pk[i] * S.pk[i];
-            S.pk[i] = S.gnew[i] - S.gfk[i];  // yk
+            const double yi = S.gnew[i] - S.gfk[i];
+            S.pk[i] = yi;  // yk (pk is free until the next iteration)
             S.gfk[i] = S.gnew[i];
             S.xk[i] = S.xt[i];
             xn2 += S.xk[i] * S.xk[i];
+            ys += yi * S.Hy[i];
             if (nan_d(S.gfk[i])) gnan = true;
             if (abs_d(S.gfk[i]) > gm) gm = abs_d(S.gfk[i]);
           }
+          pn2 = Lanes::sum(pn2);
+          xn2 = Lanes::sum(xn2);
+          const double rhok_inv = Lanes::sum(ys);
+          gm = Lanes::maxv(gm);
+          gnan = Lanes::any(gnan);
           S.it += 1;
           S.gnorm = gnan ? ::nan("") : gm;
           if (S.gnorm <= O.gtol) break;
@@ -716,37 +768,35 @@ VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
           // BFGS update of the inverse Hessian (_optimize.py:1496-1499)
           //   H <- A1 (H A2) + rho s s^T,  A1 = I - rho s y^T,  A2 = I - rho y s^T
           // evaluated as the two products scipy forms, using their rank-one structure:
-          //   T = H A2      = H - rho (H y) s^T
-          //   A1 T          = T - rho s (y^T T)
+          //   T = H A2      = H - rho (H y) s^T        (row i on lane i)
+          //   A1 T          = T - rho s (y^T T)        (column sums on lane j, rows on lane i)
           const double* sk = S.Hy;
           const double* yk = S.pk;
-          double rhok_inv = 0.0;
-          for (int i = 0; i < k; ++i) rhok_inv += yk[i] * sk[i];
           const double rhok = (rhok_inv == 0.0) ? 1000.0 : 1.0 / rhok_inv;
-          double* u = S.gnew;  // free until the next line search
-          double* w = S.xt;    // free until the next line search
-          for (int i = 0; i < k; ++i) {
-            double a1 = 0.0;
-            for (int j = 0; j < k; ++j) a1 += S.H[i * k + j] * yk[j];
-            u[i] = a1;
+          double* w = S.xt;  // free until the next line search
+          Lanes::sync();     // yk, sk complete
+          VSR_FOR_K(i, k) {
+            double ui = 0.0;
+            for (int j = 0; j < k; ++j) ui += S.H[i * k + j] * yk[j];
+            for (int j = 0; j < k; ++j) S.H[i * k + j] -= rhok * ui * sk[j];
           }
-          for (int i = 0; i < k; ++i)
-            for (int j = 0; j < k; ++j) S.H[i * k + j] -= rhok * u[i] * sk[j];
-          for (int j = 0; j < k; ++j) {
+          Lanes::sync();  // T complete
+          VSR_FOR_K(j, k) {
             double a2 = 0.0;
             for (int l = 0; l < k; ++l) a2 += yk[l] * S.H[l * k + j];
             w[j] = a2;
           }
-          for (int i = 0; i < k; ++i)
-            for (int j = 0; j < k; ++j)
-              S.H[i * k + j] += rhok * sk[i] * sk[j] - rhok * sk[i] * w[j];
+          Lanes::sync();  // w complete
+          VSR_FOR_K(i, k) {
+            for (int j = 0; j < k; ++j) S.H[i * k + j] += rhok * sk[i] * sk[j] - rhok * sk[i] * w[j];
+          }
         }
       }
       // ---- termination message (_optimize.py:1503-1513) ----
       {
         bool xnan = false;
-        for (int i = 0; i < k; ++i)
-          if (nan_d(S.xk[i])) xnan = true;
+        VSR_FOR_K(i, k) if (nan_d(S.xk[i])) xnan = true;
+        xnan = Lanes::any(xnan);
         if (S.warnflag == 2)
           S.status = VSR_FIT_PRECLOSS;
         else if (S.it >= S.maxiter)

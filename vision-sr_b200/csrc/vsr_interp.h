@@ -24,34 +24,39 @@
 
 #if defined(__CUDACC__)
 #define VSR_HD __host__ __device__ __forceinline__
+// the heavy libm routines are kept OUT of line: the interpreter has ~60 handlers and P
+// copies of each; inlining pow/sin/... into all of them made the kernels 300-500 KB of
+// SASS, far beyond the instruction caches.  One copy per kernel, reached by a call.
+#define VSR_MATH __host__ __device__ __noinline__
 #else
 #include <cmath>
 #define VSR_HD inline
+#define VSR_MATH inline
 #endif
 
 namespace vsr {
 
 // ---- scalar math, overloaded on float/double ------------------------------------
-#define VSR_M1(name, fd, ff)                         \
-  VSR_HD double name(double x) { return fd(x); }     \
-  VSR_HD float name(float x) { return ff(x); }
-VSR_M1(m_sqrt, ::sqrt, ::sqrtf)
-VSR_M1(m_exp, ::exp, ::expf)
-VSR_M1(m_log, ::log, ::logf)
-VSR_M1(m_sin, ::sin, ::sinf)
-VSR_M1(m_cos, ::cos, ::cosf)
-VSR_M1(m_tan, ::tan, ::tanf)
-VSR_M1(m_asin, ::asin, ::asinf)
-VSR_M1(m_acos, ::acos, ::acosf)
-VSR_M1(m_atan, ::atan, ::atanf)
-VSR_M1(m_sinh, ::sinh, ::sinhf)
-VSR_M1(m_cosh, ::cosh, ::coshf)
-VSR_M1(m_tanh, ::tanh, ::tanhf)
-VSR_M1(m_abs, ::fabs, ::fabsf)
+#define VSR_M1(Q, name, fd, ff)                 \
+  Q double name(double x) { return fd(x); }     \
+  Q float name(float x) { return ff(x); }
+VSR_M1(VSR_HD, m_sqrt, ::sqrt, ::sqrtf)
+VSR_M1(VSR_HD, m_abs, ::fabs, ::fabsf)
+VSR_M1(VSR_MATH, m_exp, ::exp, ::expf)
+VSR_M1(VSR_MATH, m_log, ::log, ::logf)
+VSR_M1(VSR_MATH, m_sin, ::sin, ::sinf)
+VSR_M1(VSR_MATH, m_cos, ::cos, ::cosf)
+VSR_M1(VSR_MATH, m_tan, ::tan, ::tanf)
+VSR_M1(VSR_MATH, m_asin, ::asin, ::asinf)
+VSR_M1(VSR_MATH, m_acos, ::acos, ::acosf)
+VSR_M1(VSR_MATH, m_atan, ::atan, ::atanf)
+VSR_M1(VSR_MATH, m_sinh, ::sinh, ::sinhf)
+VSR_M1(VSR_MATH, m_cosh, ::cosh, ::coshf)
+VSR_M1(VSR_MATH, m_tanh, ::tanh, ::tanhf)
 #undef VSR_M1
-VSR_HD double m_pow(double a, double b) { return ::pow(a, b); }
-VSR_HD float m_pow(float a, float b) { return ::powf(a, b); }
-VSR_HD void m_sincos(double x, double* s, double* c) {
+VSR_MATH double m_pow(double a, double b) { return ::pow(a, b); }
+VSR_MATH float m_pow(float a, float b) { return ::powf(a, b); }
+VSR_MATH void m_sincos(double x, double* s, double* c) {
 #if defined(__CUDA_ARCH__)
   ::sincos(x, s, c);
 #else
@@ -59,7 +64,7 @@ VSR_HD void m_sincos(double x, double* s, double* c) {
   *c = ::cos(x);
 #endif
 }
-VSR_HD void m_sincos(float x, float* s, float* c) {
+VSR_MATH void m_sincos(float x, float* s, float* c) {
 #if defined(__CUDA_ARCH__)
   ::sincosf(x, s, c);
 #else
@@ -207,22 +212,187 @@ VSR_HD void unary_apply(Dual<T, K>& x, unsigned am, int n) {
   }
   x.v = f;
   if (K > 0) {
-    if (guard) {
+    if (guard) {  // sqrt at 0, asin/acos at +-1: an exact-zero tangent must stay zero
 #pragma unroll
-      for (int i = 0; i < K; ++i)
-        if ((am >> i) & 1u) x.d[i] = m_scale(x.d[i], fp);
-    } else {
+      for (int i = 0; i < K; ++i) x.d[i] = m_scale(x.d[i], fp);
+    } else {      // dense: a dead tangent is an exact zero and stays one for finite fp
 #pragma unroll
-      for (int i = 0; i < K; ++i)
-        if ((am >> i) & 1u) x.d[i] *= fp;
+      for (int i = 0; i < K; ++i) x.d[i] *= fp;
     }
   }
 }
 
-// Where the points come from: col(j, p) returns x_{j+1} of the p-th point of this call.
-// (a functor so the kernels can read registers/shared memory and the host simulator a
-// plain array.)
+// ---- instruction dispatch ------------------------------------------------------------------
+// The interpreter dispatches on ONE dense handler id per instruction so the compiler emits a
+// single jump table: (opcode, operand source) pairs for LOAD and the binary ops, the opcode
+// alone for everything else.  Programs are "predecoded" (handler id written over the opcode
+// byte) when they are copied into shared memory.
+#define VSR_H_BIN(op, src) (((op) << 2) | (src))  /* op in LOAD..RPOW: 4..43 */
+#define VSR_H_UN(op) (48 + (op))                   /* unary ops: 59..75 */
+#define VSR_H_END 0
+#define VSR_H_PUSH VSR_H_BIN(VSR_PUSH, 0)
+#define VSR_HANDLER(w) ((unsigned)((w)&0xff))
 
+VSR_HD vsr_insn_t predecode(vsr_insn_t w) {
+  const unsigned op = VSR_OP(w);
+  unsigned h;
+  if (op == VSR_END)
+    h = VSR_H_END;
+  else if (op == VSR_PUSH)
+    h = VSR_H_PUSH;
+  else if (op <= VSR_RPOW)
+    h = VSR_H_BIN(op, VSR_SRC(w) & 3u);
+  else
+    h = VSR_H_UN(op);
+  return (w & ~(vsr_insn_t)0xff) | (vsr_insn_t)h;
+}
+
+// LOAD / binary node with its operand source known at compile time.
+//   acc = acc (OP) b,  b = popped stack entry | column | fitted constant | literal
+// Tangent arithmetic is dense over the K tangents wherever a dead (exactly zero) tangent
+// stays zero for finite values; only stack operands and the guarded power rules consult
+// the liveness masks.  (A tangent that turns nan where the value stays finite is dropped
+// when the gradient is accumulated.)
+template <int OP, int SRC, typename T, int K, int P, typename XSrc>
+VSR_HD void binary_apply(Dual<T, K> (&acc)[P], Stack<T, K, P>& stk, int& sp, unsigned idx,
+                         unsigned am, unsigned bm, const double* __restrict__ imm,
+                         const T* __restrict__ cst, const XSrc& xs) {
+  if (SRC == VSR_SRC_STACK) --sp;
+  T ub = T(0);  // operand value when it is uniform over the points
+  if (SRC == VSR_SRC_CONST) ub = cst[idx];
+  if (SRC == VSR_SRC_IMM) ub = (T)imm[idx];
+  const unsigned lm = am | bm;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    T bv;
+    if (SRC == VSR_SRC_STACK)
+      bv = stk.s[sp][p][0];
+    else if (SRC == VSR_SRC_VAR)
+      bv = xs.col(idx, p);
+    else
+      bv = ub;
+    Dual<T, K>& x = acc[p];
+    // tangent i of the operand
+#define VSR_TB(i)                                                                   \
+  (SRC == VSR_SRC_STACK ? (((bm >> (i)) & 1u) ? stk.s[sp][p][(i) + 1] : T(0))      \
+                        : (SRC == VSR_SRC_CONST ? ((i) == (int)idx ? T(1) : T(0)) : T(0)))
+    switch (OP) {
+      case VSR_LOAD:
+        x.v = bv;
+#pragma unroll
+        for (int i = 0; i < K; ++i) x.d[i] = VSR_TB(i);
+        break;
+      case VSR_ADD:
+        x.v += bv;
+        if (SRC == VSR_SRC_STACK || SRC == VSR_SRC_CONST) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) x.d[i] += VSR_TB(i);
+        }
+        break;
+      case VSR_SUB:
+        x.v -= bv;
+        if (SRC == VSR_SRC_STACK || SRC == VSR_SRC_CONST) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) x.d[i] -= VSR_TB(i);
+        }
+        break;
+      case VSR_RSUB:
+        x.v = bv - x.v;
+#pragma unroll
+        for (int i = 0; i < K; ++i) x.d[i] = VSR_TB(i) - x.d[i];
+        break;
+      case VSR_MUL: {
+        const T a = x.v;
+        x.v = a * bv;
+        if (SRC == VSR_SRC_STACK) {
+#pragma unroll
+          for (int i = 0; i < K; ++i)
+            if ((lm >> i) & 1u) x.d[i] = x.d[i] * bv + a * VSR_TB(i);
+        } else if (SRC == VSR_SRC_CONST) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) x.d[i] = x.d[i] * bv + (i == (int)idx ? a : T(0));
+        } else {
+#pragma unroll
+          for (int i = 0; i < K; ++i) x.d[i] *= bv;
+        }
+        break;
+      }
+      case VSR_DIV: {  // acc / b
+        const T inv = T(1) / bv;
+        const T q = x.v / bv;
+        if (SRC == VSR_SRC_STACK) {
+#pragma unroll
+          for (int i = 0; i < K; ++i)
+            if ((lm >> i) & 1u) x.d[i] = (x.d[i] - q * VSR_TB(i)) * inv;
+        } else if (SRC == VSR_SRC_CONST) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) x.d[i] = (x.d[i] - (i == (int)idx ? q : T(0))) * inv;
+        } else {
+#pragma unroll
+          for (int i = 0; i < K; ++i) x.d[i] *= inv;
+        }
+        x.v = q;
+        break;
+      }
+      case VSR_RDIV: {  // b / acc
+        const T a = x.v;
+        const T inv = T(1) / a;
+        const T q = bv / a;
+        if (SRC == VSR_SRC_STACK) {
+#pragma unroll
+          for (int i = 0; i < K; ++i)
+            if ((lm >> i) & 1u) x.d[i] = (VSR_TB(i) - q * x.d[i]) * inv;
+        } else if (SRC == VSR_SRC_CONST) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) x.d[i] = ((i == (int)idx ? T(1) : T(0)) - q * x.d[i]) * inv;
+        } else {
+          const T cf = -q * inv;
+#pragma unroll
+          for (int i = 0; i < K; ++i) x.d[i] *= cf;
+        }
+        x.v = q;
+        break;
+      }
+      case VSR_POW: {  // acc ** b
+        const T a = x.v;
+        const T f = m_pow(a, bv);
+        if (K > 0 && lm) {
+          // d/da = b a^(b-1) = b f / a (one division instead of a second pow; pow again
+          // only at a == 0);  d/db = f ln a  (0 where a == 0 and the power vanishes)
+          const T fa = am ? (a != T(0) ? bv * (f / a) : bv * m_pow(a, bv - T(1))) : T(0);
+          T fb = T(0);
+          if (bm) fb = (a == T(0) && f == T(0)) ? T(0) : f * m_log(a);
+#pragma unroll
+          for (int i = 0; i < K; ++i)
+            if ((lm >> i) & 1u) x.d[i] = m_scale(x.d[i], fa) + m_scale((T)VSR_TB(i), fb);
+        }
+        x.v = f;
+        break;
+      }
+      case VSR_RPOW: {  // b ** acc
+        const T a = x.v;
+        const T f = m_pow(bv, a);
+        if (K > 0 && lm) {
+          T fa = T(0);
+          if (am) fa = (bv == T(0) && f == T(0)) ? T(0) : f * m_log(bv);
+          const T fb = bm ? (bv != T(0) ? a * (f / bv) : a * m_pow(bv, a - T(1))) : T(0);
+#pragma unroll
+          for (int i = 0; i < K; ++i)
+            if ((lm >> i) & 1u) x.d[i] = m_scale(x.d[i], fa) + m_scale((T)VSR_TB(i), fb);
+        }
+        x.v = f;
+        break;
+      }
+      default:
+        break;
+    }
+#undef VSR_TB
+  }
+}
+
+// Where the points come from: col(j, p) returns x_{j+1} of the p-th point of this call.
+// (a functor so the kernels can read global or shared memory and the host simulator a
+// plain array.)  `prog` must be predecoded.
 template <typename T, int K, int P, typename XSrc>
 VSR_HD void eval_points(const vsr_insn_t* __restrict__ prog, const double* __restrict__ imm,
                         const T* __restrict__ cst, const XSrc& xs, Dual<T, K> (&acc)[P],
@@ -236,193 +406,67 @@ VSR_HD void eval_points(const vsr_insn_t* __restrict__ prog, const double* __res
   }
   for (int pc = 0;; ++pc) {
     const vsr_insn_t w = prog[pc];
-    const unsigned op = VSR_OP(w);
-    if (op == VSR_END) break;
+    const unsigned idx = VSR_IDX(w);
     const unsigned am = VSR_AMASK(w);
     const unsigned bm = VSR_BMASK(w);
-    const unsigned lm = am | bm;
-    (void)lm;
-
-    if (op == VSR_PUSH) {
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        stk.s[sp][p][0] = acc[p].v;
-#pragma unroll
-        for (int i = 0; i < K; ++i)
-          if ((am >> i) & 1u) stk.s[sp][p][i + 1] = acc[p].d[i];
-      }
-      ++sp;
-      continue;
-    }
-
-    if (op <= VSR_RPOW) {  // LOAD and the binary ops: fetch the operand first
-      const unsigned src = VSR_SRC(w);
-      const unsigned idx = VSR_IDX(w);
-      T bv[P];
-      T bd[P][K > 0 ? K : 1];
-#pragma unroll
-      for (int p = 0; p < P; ++p)
-#pragma unroll
-        for (int i = 0; i < (K > 0 ? K : 1); ++i) bd[p][i] = T(0);
-      if (src == VSR_SRC_STACK) {
-        --sp;
+    switch (VSR_HANDLER(w)) {
+      case VSR_H_END:
+        return;
+      case VSR_H_PUSH:
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-          bv[p] = stk.s[sp][p][0];
+          stk.s[sp][p][0] = acc[p].v;
 #pragma unroll
           for (int i = 0; i < K; ++i)
-            if ((bm >> i) & 1u) bd[p][i] = stk.s[sp][p][i + 1];
+            if ((am >> i) & 1u) stk.s[sp][p][i + 1] = acc[p].d[i];
         }
-      } else if (src == VSR_SRC_VAR) {
-#pragma unroll
-        for (int p = 0; p < P; ++p) bv[p] = xs.col(idx, p);
-      } else if (src == VSR_SRC_CONST) {
-        const T c = cst[idx];
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-          bv[p] = c;
-#pragma unroll
-          for (int i = 0; i < K; ++i) bd[p][i] = (i == (int)idx) ? T(1) : T(0);
-        }
-      } else {
-        const T c = (T)imm[idx];
-#pragma unroll
-        for (int p = 0; p < P; ++p) bv[p] = c;
-      }
-
-      switch (op) {
-        case VSR_LOAD:
-#pragma unroll
-          for (int p = 0; p < P; ++p) {
-            acc[p].v = bv[p];
-#pragma unroll
-            for (int i = 0; i < K; ++i) acc[p].d[i] = bd[p][i];
-          }
-          break;
-        case VSR_ADD:
-#pragma unroll
-          for (int p = 0; p < P; ++p) {
-            acc[p].v += bv[p];
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-              if ((bm >> i) & 1u) acc[p].d[i] += bd[p][i];
-          }
-          break;
-        case VSR_SUB:
-#pragma unroll
-          for (int p = 0; p < P; ++p) {
-            acc[p].v -= bv[p];
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-              if ((bm >> i) & 1u) acc[p].d[i] -= bd[p][i];
-          }
-          break;
-        case VSR_RSUB:
-#pragma unroll
-          for (int p = 0; p < P; ++p) {
-            acc[p].v = bv[p] - acc[p].v;
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-              if ((lm >> i) & 1u) acc[p].d[i] = bd[p][i] - acc[p].d[i];
-          }
-          break;
-        case VSR_MUL:
-#pragma unroll
-          for (int p = 0; p < P; ++p) {
-            const T a = acc[p].v;
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-              if ((lm >> i) & 1u) acc[p].d[i] = acc[p].d[i] * bv[p] + a * bd[p][i];
-            acc[p].v = a * bv[p];
-          }
-          break;
-        case VSR_DIV:  // acc / b
-#pragma unroll
-          for (int p = 0; p < P; ++p) {
-            const T q = acc[p].v / bv[p];
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-              if ((lm >> i) & 1u) acc[p].d[i] = (acc[p].d[i] - q * bd[p][i]) / bv[p];
-            acc[p].v = q;
-          }
-          break;
-        case VSR_RDIV:  // b / acc
-#pragma unroll
-          for (int p = 0; p < P; ++p) {
-            const T a = acc[p].v;
-            const T q = bv[p] / a;
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-              if ((lm >> i) & 1u) acc[p].d[i] = (bd[p][i] - q * acc[p].d[i]) / a;
-            acc[p].v = q;
-          }
-          break;
-        case VSR_POW:  // acc ** b
-#pragma unroll
-          for (int p = 0; p < P; ++p) {
-            const T a = acc[p].v;
-            const T f = m_pow(a, bv[p]);
-            if (K > 0 && lm) {
-              // d/da = b a^(b-1);  d/db = f ln a  (0 where a == 0 and the power vanishes)
-              const T fa = am ? bv[p] * m_pow(a, bv[p] - T(1)) : T(0);
-              T fb = T(0);
-              if (bm) fb = (a == T(0) && f == T(0)) ? T(0) : f * m_log(a);
-#pragma unroll
-              for (int i = 0; i < K; ++i)
-                if ((lm >> i) & 1u)
-                  acc[p].d[i] = m_scale(acc[p].d[i], fa) + m_scale(bd[p][i], fb);
-            }
-            acc[p].v = f;
-          }
-          break;
-        case VSR_RPOW:  // b ** acc
-#pragma unroll
-          for (int p = 0; p < P; ++p) {
-            const T a = acc[p].v;
-            const T f = m_pow(bv[p], a);
-            if (K > 0 && lm) {
-              T fa = T(0);
-              if (am) fa = (bv[p] == T(0) && f == T(0)) ? T(0) : f * m_log(bv[p]);
-              const T fb = bm ? a * m_pow(bv[p], a - T(1)) : T(0);
-#pragma unroll
-              for (int i = 0; i < K; ++i)
-                if ((lm >> i) & 1u)
-                  acc[p].d[i] = m_scale(acc[p].d[i], fa) + m_scale(bd[p][i], fb);
-            }
-            acc[p].v = f;
-          }
-          break;
-        default:
-          break;
-      }
-      continue;
-    }
-
-    // unary ops on acc: v = f(v), d *= f'(v).  The dispatch is outside the loop over
-    // the P points so one decode serves all of them.
-    switch (op) {
-#define VSR_UCASE(OPC)                                                  \
-  case OPC:                                                             \
-    _Pragma("unroll") for (int p = 0; p < P; ++p)                       \
-        unary_apply<OPC, T, K>(acc[p], am, (int)(int16_t)VSR_IDX(w));   \
+        ++sp;
+        break;
+#define VSR_BCASE(OPC)                                                                          \
+  case VSR_H_BIN(OPC, VSR_SRC_STACK):                                                           \
+    binary_apply<OPC, VSR_SRC_STACK, T, K, P>(acc, stk, sp, idx, am, bm, imm, cst, xs);         \
+    break;                                                                                      \
+  case VSR_H_BIN(OPC, VSR_SRC_VAR):                                                             \
+    binary_apply<OPC, VSR_SRC_VAR, T, K, P>(acc, stk, sp, idx, am, bm, imm, cst, xs);           \
+    break;                                                                                      \
+  case VSR_H_BIN(OPC, VSR_SRC_CONST):                                                           \
+    binary_apply<OPC, VSR_SRC_CONST, T, K, P>(acc, stk, sp, idx, am, bm, imm, cst, xs);         \
+    break;                                                                                      \
+  case VSR_H_BIN(OPC, VSR_SRC_IMM):                                                             \
+    binary_apply<OPC, VSR_SRC_IMM, T, K, P>(acc, stk, sp, idx, am, bm, imm, cst, xs);           \
     break;
-      VSR_UCASE(VSR_NEG)
-      VSR_UCASE(VSR_ABS)
-      VSR_UCASE(VSR_SIGN)
-      VSR_UCASE(VSR_INV)
-      VSR_UCASE(VSR_SQRT)
-      VSR_UCASE(VSR_EXP)
-      VSR_UCASE(VSR_LOG)
-      VSR_UCASE(VSR_SIN)
-      VSR_UCASE(VSR_COS)
-      VSR_UCASE(VSR_TAN)
-      VSR_UCASE(VSR_ASIN)
-      VSR_UCASE(VSR_ACOS)
-      VSR_UCASE(VSR_ATAN)
-      VSR_UCASE(VSR_SINH)
-      VSR_UCASE(VSR_COSH)
-      VSR_UCASE(VSR_TANH)
-      VSR_UCASE(VSR_POWI)
+        VSR_BCASE(VSR_LOAD)
+        VSR_BCASE(VSR_ADD)
+        VSR_BCASE(VSR_SUB)
+        VSR_BCASE(VSR_RSUB)
+        VSR_BCASE(VSR_MUL)
+        VSR_BCASE(VSR_DIV)
+        VSR_BCASE(VSR_RDIV)
+        VSR_BCASE(VSR_POW)
+        VSR_BCASE(VSR_RPOW)
+#undef VSR_BCASE
+#define VSR_UCASE(OPC)                                                  \
+  case VSR_H_UN(OPC):                                                   \
+    _Pragma("unroll") for (int p = 0; p < P; ++p)                       \
+        unary_apply<OPC, T, K>(acc[p], am, (int)(int16_t)idx);          \
+    break;
+        VSR_UCASE(VSR_NEG)
+        VSR_UCASE(VSR_ABS)
+        VSR_UCASE(VSR_SIGN)
+        VSR_UCASE(VSR_INV)
+        VSR_UCASE(VSR_SQRT)
+        VSR_UCASE(VSR_EXP)
+        VSR_UCASE(VSR_LOG)
+        VSR_UCASE(VSR_SIN)
+        VSR_UCASE(VSR_COS)
+        VSR_UCASE(VSR_TAN)
+        VSR_UCASE(VSR_ASIN)
+        VSR_UCASE(VSR_ACOS)
+        VSR_UCASE(VSR_ATAN)
+        VSR_UCASE(VSR_SINH)
+        VSR_UCASE(VSR_COSH)
+        VSR_UCASE(VSR_TANH)
+        VSR_UCASE(VSR_POWI)
 #undef VSR_UCASE
       default:
         break;

@@ -1,9 +1,11 @@
 // vsr_kernels.cuh -- sm_100a kernels of the refinement engine.
 //
-//   fit_kernel<T,K,P>   one CTA per (candidate, restart) run: thread 0 advances the BFGS
-//                       state machine (vsr_bfgs.h), all threads sweep the points through
-//                       the interpreter (vsr_interp.h) whenever it asks for the objective.
-//                       Replaces minimize(safe_loss, x0, 'BFGS') + the lambdified loss
+//   fit_kernel<T,K,P>   one thread-block CLUSTER per (candidate, restart) run: thread 0 of the
+//                       leader CTA advances the BFGS state machine (vsr_bfgs.h); whenever it
+//                       asks for the objective all threads of all CTAs sweep their slice of
+//                       the points -- TMA-staged once into distributed shared memory --
+//                       through the interpreter (vsr_interp.h).  Replaces
+//                       minimize(safe_loss, x0, 'BFGS') + the lambdified loss
 //                       (reference bfgs.py:102-118).
 //   eval_kernel<T,K,P>  batched loss (+ gradient) of (program, constants) pairs; grid.y
 //                       splits the points.  Replaces bfgs.py:106-112 and :120-132.
@@ -16,6 +18,7 @@
 #ifndef VSR_KERNELS_CUH_
 #define VSR_KERNELS_CUH_
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -52,6 +55,10 @@ struct FitArgs {
   double* out_lastx;
   double* out_loss;
   int32_t* out_info;
+  int32_t resident;      // 1: every CTA stages its slice of the points into shared memory
+  int32_t tma_ok;        // 1: column starts and strides are 16-byte aligned (bulk copies)
+  int32_t slice_stride;  // elements between columns of the staged slice
+  long long* phase_cycles;  // optional [n_slots][8]: SM cycles per phase of the pass loop (leader thread 0)
   FitOpts O;
 };
 
@@ -172,29 +179,154 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-// dynamic shared memory of fit_kernel, in doubles:
-//   ws[fit_workspace_doubles(k)] | red[nwarps*(K+1)] | cst[kmax] | imm[n_imm] | insn[n_insn]
-__host__ __device__ inline int fit_smem_doubles(int kmax, int K, int nwarps, int n_insn,
-                                                int n_imm) {
-  return fit_workspace_doubles(kmax) + nwarps * (K + 1) + kmax + n_imm + n_insn + 2;
+// ---- TMA (bulk async copy) + mbarrier primitives, sm_90+ PTX ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "VSR_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra VSR_MBAR_DONE;\n"
+      "bra VSR_MBAR_WAIT;\n"
+      "VSR_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> this CTA's shared memory, completion counted in bytes on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                              uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
 }
 
+// ---- point source: this CTA's slice, resident in shared memory ----------------------------------
+// VAR operands of the shared-memory copy of the program are rewritten to column SLOTS of
+// the slice, so col(j, p) is one LDS.
+template <typename T, int P>
+struct SlicePoints {
+  const T* base;  // [n_slots][stride]
+  int stride;
+  int idx[P];
+  __device__ __forceinline__ T col(unsigned j, int p) const { return base[j * stride + idx[p]]; }
+};
+
+// One pass over the resident slice (cnt points): s += r^2, g[t] += r * d f/d c_t.
 template <typename T, int K, int P>
-__global__ void __launch_bounds__(256) fit_kernel(const FitArgs a) {
-  extern __shared__ double smem[];
-  __shared__ FitState S;
+__device__ __forceinline__ void sweep_slice(const vsr_insn_t* prog, const double* imm, const T* cst,
+                                            const T* xs, const T* ys, int stride, int cnt, double& s,
+                                            double (&g)[K > 0 ? K : 1]) {
+  s = 0.0;
+#pragma unroll
+  for (int t = 0; t < (K > 0 ? K : 1); ++t) g[t] = 0.0;
+  const int nt = blockDim.x;
+  const int tid = threadIdx.x;
+  Stack<T, K, P> stk;
+  SlicePoints<T, P> src;
+  src.base = xs;
+  src.stride = stride;
+  for (int base = 0; base < cnt; base += nt * P) {
+    bool valid[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const int i = base + p * nt + tid;
+      valid[p] = i < cnt;
+      src.idx[p] = valid[p] ? i : (cnt - 1);
+    }
+    Dual<T, K> acc[P];
+    eval_points<T, K, P>(prog, imm, cst, src, acc, stk);
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      if (valid[p]) {
+        const double r = (double)acc[p].v - (double)ys[src.idx[p]];
+        s += r * r;
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+          const double gt = r * (double)acc[p].d[t];
+          g[t] += isfinite(gt) ? gt : 0.0;
+        }
+      }
+    }
+  }
+}
+
+// ---- fit kernel ------------------------------------------------------------------------------------
+// One thread-block CLUSTER per (candidate, restart) run.  The points are split in
+// contiguous slices, one per CTA of the cluster.  When a slice fits, its used columns and
+// y are staged ONCE into the CTA's shared memory by TMA bulk copies and stay there for
+// every pass of the run (hundreds to thousands): the whole data set lives in the
+// cluster's distributed shared memory and HBM/L2 is read once per run.  CTA 0 (the
+// leader) owns the optimiser state; per pass the other CTAs read the trial constants from
+// the leader's shared memory and write their partial sums into it (DSMEM), with two
+// cluster barriers.  Reduction order is fixed (lanes, warps, CTA rank).
+//
+// dynamic shared memory, in bytes (16-byte aligned sections):
+//   ws[fit_workspace_doubles(k)] | cred[cs*(K+1)] | red[nwarps*(K+1)] | cst[k+1] | imm | insn |
+//   slice: (n_slots + 1) * stride * sizeof(T)
+__host__ __device__ inline size_t fit_smem_bytes(int kmax, int K, int nwarps, int cs, int n_insn,
+                                                 int n_imm, int n_slots, int stride, int elem) {
+  size_t dbl = (size_t)fit_workspace_doubles(kmax) + (size_t)cs * (K + 1) + (size_t)nwarps * (K + 1) +
+               kmax + 1 + n_imm + n_insn + 2;
+  dbl = (dbl + 1) & ~(size_t)1;  // 16-byte boundary
+  return dbl * 8 + (size_t)(n_slots + 1) * stride * elem;
+}
+
+// Widest CTA the fit kernel is compiled for.  320 threads at <= 96 registers lets TWO CTAs
+// (of different clusters, i.e. different runs) share an SM: while one run's cluster sits in
+// its optimiser step or a cluster barrier the other one sweeps.
+template <typename T, int K>
+__host__ __device__ constexpr int fit_max_threads() {
+  return (sizeof(T) == 8 && K > 8) ? 256 : 320;
+}
+template <typename T, int K>
+__host__ __device__ constexpr int fit_min_ctas() {
+  return (sizeof(T) == 8 && K > 8) ? 1 : 2;
+}
+
+// The optimiser step, out of line: its register and stack needs stay out of the sweep's
+// allocation (the sweep is the hot loop; this runs on one warp between sweeps).
+__device__ __noinline__ int fit_step_call(FitState& S, const FitOpts& O) { return fit_step(S, O); }
+
+template <typename T, int K, int P>
+__global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>())) fit_kernel(const FitArgs a) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) double smem[];
+  FitState S;  // private per lane; only warp 0 of the leader CTA runs the optimiser
+  __shared__ double s_rf;
   __shared__ int s_action;
   __shared__ unsigned long long s_t0;
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_slot_of[VSR_MAX_VARS];
 
-  const int run = blockIdx.x;
-  if (run >= a.n_runs) return;
+  const int cs = (int)cluster.num_blocks();
+  const int crank = (int)cluster.block_rank();
+  const int run = blockIdx.x / cs;
   const int prog = a.run_prog[run];
   const int slot = a.run_slot[run];
   const int k = a.pt.k[prog];
   const int nw = (blockDim.x + 31) >> 5;
+  const int tid = threadIdx.x;
 
   double* ws = smem;
-  double* red = ws + fit_workspace_doubles(k);
+  double* cred = ws + fit_workspace_doubles(k);
+  double* red = cred + cs * (K + 1);
   T* cst = reinterpret_cast<T*>(red + nw * (K + 1));
   double* s_imm = red + nw * (K + 1) + k + 1;
   int n_insn, n_imm;
@@ -203,8 +335,8 @@ __global__ void __launch_bounds__(256) fit_kernel(const FitArgs a) {
   load_program(a.pt, prog, s_insn, s_imm, n_insn, n_imm);
 
   int32_t* info = a.out_info + (int64_t)slot * 4;
-  if (k == 0) {  // nothing to optimise (reference bfgs.py:117-118)
-    if (threadIdx.x == 0) {
+  if (k == 0) {  // nothing to optimise (reference bfgs.py:117-118); uniform over the cluster
+    if (crank == 0 && tid == 0) {
       info[0] = VSR_FIT_NOT_RUN;
       info[1] = 0;
       info[2] = 0;
@@ -213,29 +345,139 @@ __global__ void __launch_bounds__(256) fit_kernel(const FitArgs a) {
     }
     return;
   }
-  if (threadIdx.x == 0) {
-    fit_init(S, k, ws, a.x0 + (int64_t)slot * a.kstride);
-    s_t0 = 0ull;
-  }
-  __syncthreads();
 
+  // ---- this CTA's slice of the points ----
+  const int64_t N = a.pts.n;
+  int64_t per = (N + cs - 1) / cs;
+  per = (per + 31) & ~(int64_t)31;  // slices start on 32-point boundaries (TMA alignment)
+  int64_t n0 = (int64_t)crank * per, n1 = n0 + per;
+  n0 = n0 < N ? n0 : N;
+  n1 = n1 < N ? n1 : N;
+  const int cnt = (int)(n1 - n0);
   const T* X = static_cast<const T*>(a.pts.X);
   const T* y = static_cast<const T*>(a.pts.y);
-  const int64_t N = a.pts.n;
+
+  T* xs = nullptr;
+  T* ys = nullptr;
+  const int stride = a.slice_stride;
+  if (a.resident) {
+    size_t off = (size_t)((reinterpret_cast<char*>(s_insn + n_insn) - reinterpret_cast<char*>(smem)) + 15) &
+                 ~(size_t)15;
+    ys = reinterpret_cast<T*>(reinterpret_cast<char*>(smem) + off);
+    xs = ys + stride;
+    __syncthreads();  // program is in shared memory
+    constexpr int kAlign = 16 / (int)sizeof(T);
+    const int full = cnt & ~(kAlign - 1);  // elements per column that move as 16-byte units
+    const bool use_tma = a.tma_ok && full > 0;
+    if (tid == 0) {
+      // rewrite VAR operands to slice column slots, in first-use order
+      for (int j = 0; j < VSR_MAX_VARS; ++j) s_slot_of[j] = -1;
+      int ns = 0;
+      for (int i = 0; i < n_insn; ++i) {
+        const vsr_insn_t w = s_insn[i];
+        const unsigned op = VSR_OP(w);
+        if (op >= VSR_LOAD && op <= VSR_RPOW && op != VSR_PUSH && VSR_SRC(w) == VSR_SRC_VAR) {
+          const unsigned j = VSR_IDX(w);
+          if (s_slot_of[j] < 0) s_slot_of[j] = ns++;
+          s_insn[i] = (w & ~((vsr_insn_t)0xffff << 16)) | ((vsr_insn_t)s_slot_of[j] << 16);
+        }
+      }
+      if (use_tma) {
+        const uint32_t bytes = (uint32_t)full * (uint32_t)sizeof(T);
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&s_bar, bytes * (uint32_t)(ns + 1));
+        tma_bulk_load(ys, y + n0, bytes, &s_bar);
+        for (int j = 0; j < VSR_MAX_VARS; ++j)
+          if (s_slot_of[j] >= 0)
+            tma_bulk_load(xs + (size_t)s_slot_of[j] * stride, X + (int64_t)j * a.pts.ldx + n0, bytes, &s_bar);
+      }
+    }
+    __syncthreads();  // slot table, rewritten program and the armed barrier are visible
+    {
+      // everything TMA does not move (all of it when the caller's memory is unaligned): coalesced loads
+      const int first = use_tma ? full : 0;
+      for (int i = first + tid; i < cnt; i += blockDim.x) ys[i] = y[n0 + i];
+      for (int j = 0; j < VSR_MAX_VARS; ++j) {
+        const int sj = s_slot_of[j];
+        if (sj < 0) continue;
+        for (int i = first + tid; i < cnt; i += blockDim.x)
+          xs[(size_t)sj * stride + i] = X[(int64_t)j * a.pts.ldx + n0 + i];
+      }
+    }
+    if (use_tma) mbar_wait(&s_bar, 0);  // every thread observes the completed transaction
+    __syncthreads();
+  }
+
+  // handler ids over the opcode bytes (after the slot rewrite, which reads raw opcodes)
+  __syncthreads();
+  for (int i = tid; i < n_insn; i += blockDim.x) s_insn[i] = predecode(s_insn[i]);
+  __syncthreads();
+
+  const bool is_logic = crank == 0 && tid < 32;  // warp 0 of the leader: the optimiser
+  if (is_logic) {
+    fit_init(S, k, ws, a.x0 + (int64_t)slot * a.kstride);
+    if (tid == 0) s_t0 = 0ull;
+  }
+  // leader state is initialised and every CTA of the cluster is running before any DSMEM access
+  cluster.sync();
+
+  const int* r_action = cluster.map_shared_rank(&s_action, 0);
+  const double* r_xe = cluster.map_shared_rank(ws, 0);  // FitState.xe is the first k doubles of ws
+  double* r_cred = cluster.map_shared_rank(cred, 0);
   const double inv_n = 1.0 / (double)N;
 
+  // optional phase timing (measurement aid): cycles of the leader's thread 0 in
+  // [0] optimiser logic  [1] first cluster barrier  [2] constant broadcast  [3] sweep
+  // [4] CTA reduction  [5] second cluster barrier  [6] finalisation  [7] passes
+  const bool timing = a.phase_cycles != nullptr && crank == 0 && tid == 0;
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tprev = timing ? clock64() : 0;
+#define VSR_PHASE(i)                 \
+  if (timing) {                      \
+    const long long tn = clock64();  \
+    ph[i] += tn - tprev;             \
+    tprev = tn;                      \
+  }
+
   for (;;) {
-    if (threadIdx.x == 0) s_action = fit_step(S, a.O);
+    if (is_logic) {
+      const int act = fit_step_call(S, a.O);
+      if (tid == 0) s_action = act;
+    }
+    VSR_PHASE(0)
+    cluster.sync();
+    VSR_PHASE(1)
+    if (*r_action == VSR_DONE) break;
+    // trial constants from the leader, in the arithmetic type of the sweep
+    for (int i = tid; i < k; i += blockDim.x) cst[i] = (T)r_xe[i];
     __syncthreads();
-    if (s_action == VSR_DONE) break;
-    // constants of this evaluation, in the arithmetic type of the sweep
-    for (int i = threadIdx.x; i < k; i += blockDim.x) cst[i] = (T)S.xe[i];
-    __syncthreads();
+    VSR_PHASE(2)
     double s, g[K > 0 ? K : 1];
-    sweep_points<T, K, P>(s_insn, s_imm, cst, X, y, a.pts.ldx, 0, N, s, g);
+    if (a.resident)
+      sweep_slice<T, K, P>(s_insn, s_imm, cst, xs, ys, stride, cnt, s, g);
+    else
+      sweep_points<T, K, P>(s_insn, s_imm, cst, X, y, a.pts.ldx, n0, n1, s, g);
+    VSR_PHASE(3)
     block_sum<K>(s, g, red);
-    if (threadIdx.x == 0) {
-      double f = a.O.loss_scale * (s * inv_n);
+    if (tid == 0) {
+      r_cred[crank * (K + 1)] = s;
+#pragma unroll
+      for (int t = 0; t < K; ++t) r_cred[crank * (K + 1) + 1 + t] = g[t];
+    }
+    VSR_PHASE(4)
+    cluster.sync();
+    VSR_PHASE(5)
+    if (crank == 0 && tid == 0) {
+      double st = 0.0, gt[K > 0 ? K : 1];
+#pragma unroll
+      for (int t = 0; t < (K > 0 ? K : 1); ++t) gt[t] = 0.0;
+      for (int r = 0; r < cs; ++r) {
+        st += cred[r * (K + 1)];
+#pragma unroll
+        for (int t = 0; t < K; ++t) gt[t] += cred[r * (K + 1) + 1 + t];
+      }
+      double f = a.O.loss_scale * (st * inv_n);
       bool bad = !isfinite(f);
       if (a.O.stop_time < 1e8) {  // TimedFun (bfgs.py:29-33): the clock starts at the first call
         const unsigned long long now = global_ns();
@@ -245,24 +487,34 @@ __global__ void __launch_bounds__(256) fit_kernel(const FitArgs a) {
           bad = true;
       }
       if (bad) {
-        S.rf = a.O.penalty;
+        s_rf = a.O.penalty;
 #pragma unroll
         for (int t = 0; t < K; ++t)
           if (t < k) S.rg[t] = 0.0;
       } else {
-        S.rf = f;
+        s_rf = f;
 #pragma unroll
         for (int t = 0; t < K; ++t)
           if (t < k) {
-            const double gv = a.O.loss_scale * (2.0 * g[t] * inv_n);
+            const double gv = a.O.loss_scale * (2.0 * gt[t] * inv_n);
             S.rg[t] = isfinite(gv) ? gv : 0.0;
           }
       }
+      ph[7] += 1;
     }
-    // thread 0 goes straight back into fit_step; the others wait at the barrier above
+    if (is_logic) {  // the response, to every lane's private optimiser state
+      __syncwarp();
+      S.rf = s_rf;
+    }
+    VSR_PHASE(6)
+    // the leader's warp 0 goes straight back into fit_step; everyone else waits at the
+    // cluster barrier above
   }
+#undef VSR_PHASE
+  if (timing)
+    for (int i = 0; i < 8; ++i) a.phase_cycles[(int64_t)slot * 8 + i] = ph[i];
 
-  if (threadIdx.x == 0) {
+  if (crank == 0 && tid == 0) {
     double* oc = a.out_consts + (int64_t)slot * a.kstride;
     double* ol = a.out_lastx + (int64_t)slot * a.kstride;
     for (int i = 0; i < k; ++i) {
@@ -275,6 +527,8 @@ __global__ void __launch_bounds__(256) fit_kernel(const FitArgs a) {
     info[2] = S.nfev;
     info[3] = 0;
   }
+  // no CTA may exit while another can still read its shared memory
+  cluster.sync();
 }
 
 // dynamic shared memory of eval_kernel, in doubles: red | cst[k] | imm | insn
@@ -296,6 +550,8 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalArgs a) {
   load_program(a.pt, prog, s_insn, s_imm, n_insn, n_imm);
   const double* c = a.consts + (int64_t)a.pair_row[pair] * a.kstride;
   for (int i = threadIdx.x; i < k; i += blockDim.x) cst[i] = (T)c[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_insn; i += blockDim.x) s_insn[i] = predecode(s_insn[i]);
   __syncthreads();
 
   const int64_t N = a.pts.n;

@@ -91,6 +91,11 @@ class Engine:
     def set_profiling(self, on):
         self._check(self.lib.vsr_set_profiling(self._h, int(bool(on))))
 
+    def set_phase_buffer(self, tensor):
+        """int64 device tensor [n_slots, 8] (or None) for per-run phase cycle counts."""
+        self._phase = tensor
+        self._check(self.lib.vsr_set_phase_buffer(self._h, _ptr(tensor)))
+
     def read_profile(self):
         """(fit_ms, fit_launches, score_ms, score_launches) since the last read."""
         out = (ctypes.c_double * 4)()

@@ -55,6 +55,7 @@ SIGNATURES = {
     "vsr_launch_count": (ctypes.c_int64, [vp]),
     "vsr_set_profiling": (ctypes.c_int, [vp, ctypes.c_int32]),
     "vsr_read_profile": (ctypes.c_int, [vp, c_f64p]),
+    "vsr_set_phase_buffer": (ctypes.c_int, [vp, vp]),
 }
 
 _lib = None
