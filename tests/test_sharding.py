@@ -1,0 +1,110 @@
+"""Sharding of a beam's runs over ranks: partition properties and the record all-gather,
+exercised with world_size 2 over gloo on the CPU (the fit itself needs a GPU; here each
+rank fills its shard from a precomputed table, which is exactly what the exchange sees)."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import torch
+
+from conftest import PKG, ROOT
+from src.visymre.engine import sharding
+
+
+def test_partition_is_a_balanced_permutation():
+    rng = np.random.RandomState(0)
+    cost = rng.randint(1, 100, size=643).astype(float)
+    for world in (1, 2, 3, 8):
+        parts = sharding.partition_runs(cost, world)
+        allidx = np.sort(np.concatenate(parts))
+        assert np.array_equal(allidx, np.arange(643))
+        loads = [cost[p].sum() for p in parts]
+        assert max(loads) - min(loads) <= cost.max() * 1.01
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def _single_gpu_answer(fm, R):
+    C = fm.shape[0] // R
+    out = []
+    for c in range(C):
+        row = fm[c * R:(c + 1) * R]
+        try:
+            out.append(int(np.nanargmin(row)))
+        except ValueError:
+            out.append(0)
+    return np.asarray(out)
+
+
+def test_merge_equals_nanargmin_single_process():
+    rng = np.random.RandomState(1)
+    C, R, kmax, world = 37, 10, 4, 4
+    fm = rng.rand(C * R)
+    fm[rng.rand(C * R) < 0.3] = np.nan
+    fm[5 * R:6 * R] = np.nan                 # an all-nan candidate
+    fm[7 * R + 2] = fm[7 * R + 6] = 0.0      # a tie
+    loss = rng.rand(C * R)
+    consts = rng.rand(C * R, kmax)
+    parts = sharding.partition_runs(rng.rand(C * R), world)
+    recs = []
+    for r in range(world):
+        mine = torch.zeros(C * R, dtype=torch.bool)
+        mine[torch.as_tensor(parts[r])] = True
+        f = torch.full((C * R,), float("nan"), dtype=torch.float64)
+        f[mine] = torch.as_tensor(fm)[mine]
+        recs.append(sharding.local_best_records(f, torch.as_tensor(loss), torch.as_tensor(consts), C, R, mine))
+    win = sharding.merge_records(torch.stack(recs))
+    want = _single_gpu_answer(fm, R)
+    assert np.array_equal(win[:, 1].numpy().astype(int), want)
+    rows = np.arange(C) * R + want
+    np.testing.assert_array_equal(win[:, 3:3 + kmax].numpy(), consts[rows])
+    np.testing.assert_array_equal(win[:, 2].numpy(), loss[rows])
+    np.testing.assert_array_equal(np.isnan(win[:, -1].numpy()), np.isnan(fm[rows]))
+
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {pkg!r})
+    import numpy as np, torch, torch.distributed as dist
+    from src.visymre.engine import sharding
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rng = np.random.RandomState(3)
+    C, R, kmax = 23, 8, 3
+    fm = rng.rand(C * R); fm[rng.rand(C * R) < 0.25] = np.nan; fm[2*R:3*R] = np.nan
+    loss = rng.rand(C * R); consts = rng.rand(C * R, kmax)
+    parts = sharding.partition_runs(rng.rand(C * R), world)
+    mine = torch.zeros(C * R, dtype=torch.bool); mine[torch.as_tensor(parts[rank])] = True
+    f = torch.full((C * R,), float("nan"), dtype=torch.float64); f[mine] = torch.as_tensor(fm)[mine]
+    rec = sharding.local_best_records(f, torch.as_tensor(loss), torch.as_tensor(consts), C, R, mine)
+    win = sharding.allgather_best(rec)
+    want = []
+    for c in range(C):
+        row = fm[c*R:(c+1)*R]
+        want.append(0 if np.all(np.isnan(row)) else int(np.nanargmin(row)))
+    assert np.array_equal(win[:, 1].numpy().astype(int), np.asarray(want)), (rank, win[:, 1], want)
+    rows = np.arange(C) * R + np.asarray(want)
+    assert np.array_equal(win[:, 3:3+kmax].numpy(), consts[rows])
+    # every rank holds the same winners
+    gathered = [torch.empty_like(win) for _ in range(world)]
+    dist.all_gather(gathered, win)
+    assert all(torch.equal(g, gathered[0]) or (torch.isnan(g) == torch.isnan(gathered[0])).all() for g in gathered)
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+""")
+
+
+def test_allgather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(pkg=PKG))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         capture_output=True, text=True, env=env, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2

@@ -56,6 +56,21 @@ VSR_M1(VSR_MATH, m_tanh, ::tanh, ::tanhf)
 #undef VSR_M1
 VSR_MATH double m_pow(double a, double b) { return ::pow(a, b); }
 VSR_MATH float m_pow(float a, float b) { return ::powf(a, b); }
+// a**b together with ln(a) for a > 0: exp(b ln a).  libm's pow carries ln(a) in
+// double-double (~250 instructions in fp64); here the relative error of the result is
+// |b ln a| ulp of ln plus an ulp of exp, i.e. at most ~1.6e-13 (|b ln a| <= 709), inside the
+// 1e-12 budget, and the tangent rules need ln(a) anyway.  Non-positive bases keep libm's
+// exact special cases.
+template <typename T>
+VSR_HD T m_pow_log(T a, T b, T& lna) {
+  if (a > T(0)) {
+    lna = m_log(a);
+    if (a == T(1)) return T(1);
+    return m_exp(b * lna);
+  }
+  lna = m_log(a);  // -inf at 0, nan below
+  return m_pow(a, b);
+}
 VSR_MATH void m_sincos(double x, double* s, double* c) {
 #if defined(__CUDA_ARCH__)
   ::sincos(x, s, c);
@@ -355,13 +370,16 @@ VSR_HD void binary_apply(Dual<T, K> (&acc)[P], Stack<T, K, P>& stk, int& sp, uns
       }
       case VSR_POW: {  // acc ** b
         const T a = x.v;
-        const T f = m_pow(a, bv);
+        // value-only sweeps (forward-difference parity mode, final scores) keep libm's
+        // pow: FD gradients amplify an error of 1e-13 in the loss by 1/1.5e-8
+        T lna = T(0);
+        const T f = (K == 0) ? m_pow(a, bv) : m_pow_log(a, bv, lna);
         if (K > 0 && lm) {
           // d/da = b a^(b-1) = b f / a (one division instead of a second pow; pow again
           // only at a == 0);  d/db = f ln a  (0 where a == 0 and the power vanishes)
           const T fa = am ? (a != T(0) ? bv * (f / a) : bv * m_pow(a, bv - T(1))) : T(0);
           T fb = T(0);
-          if (bm) fb = (a == T(0) && f == T(0)) ? T(0) : f * m_log(a);
+          if (bm) fb = (a == T(0) && f == T(0)) ? T(0) : f * lna;
 #pragma unroll
           for (int i = 0; i < K; ++i)
             if ((lm >> i) & 1u) x.d[i] = m_scale(x.d[i], fa) + m_scale((T)VSR_TB(i), fb);
@@ -371,10 +389,11 @@ VSR_HD void binary_apply(Dual<T, K> (&acc)[P], Stack<T, K, P>& stk, int& sp, uns
       }
       case VSR_RPOW: {  // b ** acc
         const T a = x.v;
-        const T f = m_pow(bv, a);
+        T lnb = T(0);
+        const T f = (K == 0) ? m_pow(bv, a) : m_pow_log(bv, a, lnb);
         if (K > 0 && lm) {
           T fa = T(0);
-          if (am) fa = (bv == T(0) && f == T(0)) ? T(0) : f * m_log(bv);
+          if (am) fa = (bv == T(0) && f == T(0)) ? T(0) : f * lnb;
           const T fb = bm ? (bv != T(0) ? a * (f / bv) : a * m_pow(bv, a - T(1))) : T(0);
 #pragma unroll
           for (int i = 0; i < K; ++i)

@@ -211,6 +211,15 @@ class _Lowering:
                 return "unary", ("VSR_SQRT", base)
             if ex == sp.Rational(-1, 2):
                 return "unary", ("VSR_INV", sp.Pow(base, sp.Rational(1, 2), evaluate=False))
+            # half-integer powers: sqrt(x)**p, cheaper than pow and as accurate (numpy calls
+            # pow(x, p/2); the two agree to an ulp or two)
+            half = None
+            if isinstance(ex, sp.Rational) and ex.q == 2:
+                half = int(ex.p)
+            elif isinstance(ex, sp.Float) and float(ex) * 2 == int(float(ex) * 2) and float(ex) != int(float(ex)):
+                half = int(float(ex) * 2)
+            if half is not None and 1 < abs(half) <= 15:
+                return "unary", ("VSR_POWI", sp.Pow(base, sp.Rational(1, 2), evaluate=False), half)
             return "binary", ("VSR_POW", base, ex)
         if isinstance(node, sp.exp):
             return "unary", ("VSR_EXP", node.args[0])
