@@ -326,6 +326,26 @@ def main():
             h2d = Xc.nbytes + yh.nbytes + insns.nbytes + imms.nbytes + insn_off.nbytes + imm_off.nbytes + ks.nbytes + x0h.nbytes + rp.nbytes // 2 + rs.nbytes // 2
             d2h = sum(v.nbytes for v in out.values())
 
+    # ---- the Python entry point a driver calls: tokens in, dict out (sympy compile + fit +
+    #      winner formatting), a few beams, cold compile cache ----
+    api_ms, api_n = 0.0, 0
+    if rank == 0:
+        from src.visymre.architectures.model import refine_hypotheses
+        from src.visymre.workloads import generator as g
+        td = g.make_test_data()
+        cfg = g.make_cfg(R, C, grad_mode=args.grad_mode)
+        for i in range(min(args.steps, 4)):
+            b = beams[args.warmup + i]
+            Xd = torch.from_numpy(b.X[None]).to(dev)
+            yd = torch.from_numpy(b.y).reshape(1, -1, 1).to(dev)
+            hyps = [(-float(j), t) for j, t in enumerate(b.tokens)]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = refine_hypotheses(hyps, Xd, yd, cfg, td, x0=b.x0)
+            torch.cuda.synchronize()
+            api_ms += (time.perf_counter() - t0) * 1e3
+            api_n += len(out["all_bfgs_preds"])
+
     # ---- max over ranks ----
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     agg = torch.tensor([float(launches), flops, pevals, abytes, fit_ms, fit_n, score_ms], dtype=torch.float64, device=dev)
@@ -368,6 +388,9 @@ def main():
             "e2e": {"value": world * args.steps * C / (e2e_ms_max / 1e3), "unit": "candidate-fits/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "path": "vsr_upload_points + vsr_upload_programs + vsr_fit_host (C ABI, host buffers)"},
+            "api_e2e": {"value": api_n / (api_ms / 1e3) if api_ms else None, "unit": "candidate-fits/s",
+                        "path": "refine_hypotheses(token ids, X, y, cfg, test_data): sympy compile (cold cache) + "
+                                "fit + prune + winner formatting, single process"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {

@@ -220,3 +220,34 @@ def test_fit_host_equals_fit_device(eng):
     np.testing.assert_array_equal(host["loss"], dev.loss.cpu().numpy())
     np.testing.assert_array_equal(host["info"], dev.info.cpu().numpy())
     assert np.all(host["final_mse"] < 1e-10)
+
+
+def test_stop_time_zero_flattens_the_objective_like_timedfun(eng):
+    """TimedFun (bfgs.py:23-36): the clock starts at the first loss call; once stop_time has
+    passed every later call is the 1e6 penalty.  stop_time = 0 makes that deterministic."""
+    from conftest import make_cfg, make_test_data
+    rng = np.random.RandomState(3)
+    X = np.zeros((1, 80, 10))
+    X[0, :, 0] = rng.uniform(-2, 2, 80)
+    y = 1.0 + 2.0 * X[0, :, 0]
+    expr, k = "c0 + c1*x_1", 2
+    eng.set_points(X[0], y, dtypes=(fitter.F64,), n_vars=1)
+    eng.set_programs([compile_skeleton(expr, k, VARS)])
+    x0 = np.array([[3.0, -4.0], [0.5, 0.25]])
+    res = eng.fit([0, 0], [0, 1], x0, fitter.default_opts(grad_mode=FD, stop_time=0.0))
+    loss, info = res.loss.cpu().numpy(), res.info.cpu().numpy()
+    # the oracle with the same rule
+    import sympy as sp
+    from scipy.optimize import minimize
+    f = sp.lambdify(sp.symbols("c0 c1 x_1"), sp.sympify(expr), modules=vectorised.MODULES)
+    for r in range(2):
+        calls = {"n": 0}
+
+        def timed(c):
+            calls["n"] += 1
+            if calls["n"] > 1:
+                return 1e6
+            return float(np.mean((f(*c, X[0, :, 0]) - y) ** 2))
+        ref = minimize(timed, x0[r], method="BFGS")
+        assert loss[r] == pytest.approx(ref.fun, rel=1e-12)
+        assert info[r, 1] == ref.nit and info[r, 2] == ref.nfev

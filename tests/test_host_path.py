@@ -1,0 +1,107 @@
+"""Host side of the drop-in: token/string rules, workload generator, formatting, caching.
+No GPU: everything up to (and after) the fit."""
+import numpy as np
+import pytest
+import sympy as sp
+
+from oracle import vectorised
+from src.visymre.architectures import bfgs as vbfgs
+from src.visymre.architectures import data as vdata
+from src.visymre.architectures.model import analyze_prefix_tree_context, BINARY_NAMES, UNARY_NAMES
+from src.visymre.dataset.generator import Generator, InvalidPrefixExpression
+from src.visymre.workloads import generator as wg
+
+
+@pytest.fixture(scope="module")
+def beams():
+    return wg.feynman_beams(n_points=64, n_cand=24, n_restarts=3, limit=4)
+
+
+def test_skeleton_string_equals_the_oracles_independent_rules(beams, golden, test_data):
+    bs, td = beams
+    cfg = wg.make_cfg(3)
+    for b in bs:
+        for ids in b.tokens:
+            assert vbfgs.skeleton_string(ids, cfg, td) == vectorised.skeleton_string(ids, td.id2word)
+    for case in golden["cases"]:
+        if case["raised"]:
+            with pytest.raises(InvalidPrefixExpression):
+                vbfgs.skeleton_string(case["tokens"], cfg, test_data)
+        else:
+            assert vbfgs.skeleton_string(case["tokens"], cfg, test_data)[0] == case["skeleton"]
+
+
+def test_variable_shift_rule():
+    # bfgs.py:11-21: x_i -> x_{i-1} for i = 2..5 when x_{i-1} is absent, applied in order
+    assert vbfgs.replace_illegal_variables("(c0)/(x_2)") == "(c0)/(x_1)"
+    assert vbfgs.replace_illegal_variables("x_1+x_3") == "x_1+x_2"
+    assert vbfgs.replace_illegal_variables("x_2*x_3") == "x_1*x_3"   # only x_2 moves (x_2 was present)
+    assert vbfgs.replace_illegal_variables("x_7") == "x_7"
+    with pytest.raises(ValueError):
+        vbfgs.replace_illegal_variables("x_0+1")
+
+
+def test_one_pass_substitution_prints_like_the_references_sequence(beams):
+    bs, td = beams
+    cfg = wg.make_cfg(3)
+    rng = np.random.RandomState(0)
+    for b in bs:
+        for ids in b.tokens:
+            expr, k, prog = vbfgs._compile_candidate(ids, cfg, td, td.total_variables)
+            vals = list(rng.randn(k) * 3)
+            syms = [sp.Symbol(f"c{i}") for i in range(k)]
+            assert str(vbfgs._substitute(prog.expr, syms, vals)) == \
+                str(vbfgs._substitute_like_reference(expr, syms, vals))
+
+
+def test_compile_cache_hits(beams):
+    bs, td = beams
+    cfg = wg.make_cfg(3)
+    a = vbfgs._compile_candidate(bs[0].tokens[0], cfg, td, td.total_variables)
+    b = vbfgs._compile_candidate(list(bs[0].tokens[0]), cfg, td, td.total_variables)
+    assert a is b
+
+
+def test_tokens_roundtrip_and_sanitize(test_data):
+    w2i = test_data.word2id
+    words = ["add", "c", "mul", "x_1", "sin", "x_10"]
+    ids = vdata.tokenize(words, w2i)
+    assert ids[0] == w2i["S"] and ids[-1] == w2i["F"]
+    back = vdata.de_tokenize(ids[1:], {v: k for k, v in w2i.items()})
+    assert back == words
+    assert vdata.sanitize_prefix(["3", "12", "-4", "2.5", "1e-3", "I", "x_1"]) == ["3", "c", "-4", "c", "c", "c", "x_1"]
+    expr, orig = vdata.constants_to_placeholder("2.5*x_1 + 11*x_2 + 3")
+    assert str(expr) == "c*x_1 + c*x_2 + 3"
+
+
+def test_prefix_infix_and_valency(test_data):
+    w2i = test_data.word2id
+    a1 = {w2i[n] for n in UNARY_NAMES}
+    a2 = {w2i[n] for n in BINARY_NAMES}
+    good = [w2i[w] for w in "S add c mul c sin x_1".split()]
+    bad = [w2i[w] for w in "S add c mul c".split()]
+    assert analyze_prefix_tree_context(good, a1, a2, set(), w2i["pow"], None, w2i["S"])[0] == 0
+    assert analyze_prefix_tree_context(bad, a1, a2, set(), w2i["pow"], None, w2i["S"])[0] == 1
+    # no_c_in_pow: the exponent slot of pow forbids the constant token
+    half = [w2i[w] for w in "S pow x_1".split()]
+    val, forb = analyze_prefix_tree_context(half, a1, a2, set(), w2i["pow"], w2i["c"], w2i["S"])
+    assert val == 1 and w2i["c"] in forb
+    assert Generator.prefix_to_infix(["mul", "c", "pow", "x_1", "2"], coefficients=["c"],
+                                     variables=["x_1"]) == "(({c})*((x_1)**(2)))"
+    with pytest.raises(InvalidPrefixExpression):
+        Generator.prefix_to_infix(["add", "x_1", "x_2", "x_3"], coefficients=[], variables=[])
+    assert Generator.sympy_to_prefix(sp.sympify("sqrt(x_1)*3/2")) == ["mul", "div", "3", "2", "sqrt", "x_1"]
+
+
+def test_workload_is_seeded_and_well_formed(beams):
+    bs, td = beams
+    again, _ = wg.feynman_beams(n_points=64, n_cand=24, n_restarts=3, limit=4)
+    for b, b2 in zip(bs, again):
+        assert b.tokens == b2.tokens
+        np.testing.assert_array_equal(b.X, b2.X)
+        for u, v in zip(b.x0, b2.x0):
+            np.testing.assert_array_equal(u, v)
+        assert b.X.shape == (64, 10) and np.all(np.isfinite(b.y))
+        assert len(set(map(tuple, b.tokens))) == len(b.tokens) == 24
+        progs = wg.compile_beam(b, td)
+        assert all(p.k == x.shape[1] and p.k <= 8 for p, x in zip(progs, b.x0))

@@ -242,10 +242,14 @@ VSR_HD void unary_apply(Dual<T, K>& x, unsigned am, int n) {
 // single jump table: (opcode, operand source) pairs for LOAD and the binary ops, the opcode
 // alone for everything else.  Programs are "predecoded" (handler id written over the opcode
 // byte) when they are copied into shared memory.
-#define VSR_H_BIN(op, src) (((op) << 2) | (src))  /* op in LOAD..RPOW: 4..43 */
-#define VSR_H_UN(op) (48 + (op))                   /* unary ops: 59..75 */
+// ids are DENSE (0..54, no holes) so that the switch compiles to one indexed branch:
+//   0 END, 1 PUSH, 2..37 (LOAD, ADD..RPOW) x 4 sources, 38..54 the unary ops
+#define VSR_H_BINOP(op) ((op) == VSR_LOAD ? 0 : (op)-VSR_ADD + 1)          /* 0..8 */
+#define VSR_H_BIN(op, src) (2 + ((VSR_H_BINOP(op)) << 2) + (src))          /* 2..37 */
+#define VSR_H_UN(op) (38 + (op)-VSR_NEG)                                   /* 38..54 */
 #define VSR_H_END 0
-#define VSR_H_PUSH VSR_H_BIN(VSR_PUSH, 0)
+#define VSR_H_PUSH 1
+#define VSR_H_COUNT 55
 #define VSR_HANDLER(w) ((unsigned)((w)&0xff))
 
 VSR_HD vsr_insn_t predecode(vsr_insn_t w) {

@@ -153,12 +153,15 @@ __device__ __forceinline__ void block_sum(double& s, double (&g)[K > 0 ? K : 1],
     for (int t = 0; t < K; ++t) red[warp * (K + 1) + 1 + t] = g[t];
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < nw; ++w) {
-      s += red[w * (K + 1)];
+  if (warp == 0) {
+    // component `lane` summed over the warps in order 0..nw-1 (fixed order), then handed
+    // to thread 0
+    double acc = 0.0;
+    if (lane <= K)
+      for (int w = 0; w < nw; ++w) acc += red[w * (K + 1) + lane];
+    s = __shfl_sync(0xffffffffu, acc, 0);
 #pragma unroll
-      for (int t = 0; t < K; ++t) g[t] += red[w * (K + 1) + 1 + t];
-    }
+    for (int t = 0; t < K; ++t) g[t] = __shfl_sync(0xffffffffu, acc, t + 1);
   }
 }
 
@@ -468,39 +471,31 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
     VSR_PHASE(4)
     cluster.sync();
     VSR_PHASE(5)
-    if (crank == 0 && tid == 0) {
-      double st = 0.0, gt[K > 0 ? K : 1];
-#pragma unroll
-      for (int t = 0; t < (K > 0 ? K : 1); ++t) gt[t] = 0.0;
-      for (int r = 0; r < cs; ++r) {
-        st += cred[r * (K + 1)];
-#pragma unroll
-        for (int t = 0; t < K; ++t) gt[t] += cred[r * (K + 1) + 1 + t];
-      }
-      double f = a.O.loss_scale * (st * inv_n);
+    if (is_logic) {
+      // component `tid` of (sum r^2, sum r df/dc_t) over the CTAs of the cluster in rank
+      // order; lane 0 applies the penalty rule, lanes 1..k scale the gradient
+      double tot = 0.0;
+      if (tid <= K)
+        for (int r = 0; r < cs; ++r) tot += cred[r * (K + 1) + tid];
+      const double f = a.O.loss_scale * (__shfl_sync(0xffffffffu, tot, 0) * inv_n);
       bool bad = !isfinite(f);
       if (a.O.stop_time < 1e8) {  // TimedFun (bfgs.py:29-33): the clock starts at the first call
-        const unsigned long long now = global_ns();
-        if (s_t0 == 0ull)
-          s_t0 = now;
-        else if ((double)(now - s_t0) * 1e-9 >= a.O.stop_time)
-          bad = true;
+        int late = 0;
+        if (tid == 0) {
+          const unsigned long long now = global_ns();
+          if (s_t0 == 0ull)
+            s_t0 = now;
+          else if ((double)(now - s_t0) * 1e-9 >= a.O.stop_time)
+            late = 1;
+        }
+        if (__shfl_sync(0xffffffffu, late, 0)) bad = true;
       }
-      if (bad) {
-        s_rf = a.O.penalty;
-#pragma unroll
-        for (int t = 0; t < K; ++t)
-          if (t < k) S.rg[t] = 0.0;
-      } else {
-        s_rf = f;
-#pragma unroll
-        for (int t = 0; t < K; ++t)
-          if (t < k) {
-            const double gv = a.O.loss_scale * (2.0 * gt[t] * inv_n);
-            S.rg[t] = isfinite(gv) ? gv : 0.0;
-          }
+      if (tid == 0) s_rf = bad ? a.O.penalty : f;
+      if (tid >= 1 && tid <= K && tid - 1 < k) {
+        const double gv = a.O.loss_scale * (2.0 * tot * inv_n);
+        S.rg[tid - 1] = (bad || !isfinite(gv)) ? 0.0 : gv;
       }
-      ph[7] += 1;
+      if (tid == 0) ph[7] += 1;
     }
     if (is_logic) {  // the response, to every lane's private optimiser state
       __syncwarp();

@@ -93,11 +93,45 @@ def _engine_opts(cfg, scale, eval_dtype, score_dtype):
 
 
 def _substitute(expr, symbols, values):
-    """bfgs.py:120-124: put the numbers in, one constant after the other."""
-    final = expr
+    """bfgs.py:120-124: put the numbers in.
+
+    The reference re-sympifies its string and calls ``.replace(symbol, value)`` once per
+    constant (~10 ms a time).  ``xreplace`` on the already-sympified skeleton, one constant
+    after the other in the same order, rebuilds the same trees -- the values go through the
+    same ``sympify`` conversion and the Floats combine in the same order -- and prints the
+    same string (tests/test_host_path.py checks this on the workload's candidates)."""
+    final = sp.sympify(expr)
+    for s, v in zip(symbols, values):
+        final = final.xreplace({s: sp.sympify(v)})
+    return final
+
+
+def _substitute_like_reference(expr_str, symbols, values):
+    """The reference's own sequence, kept for the equivalence test."""
+    final = expr_str
     for s, v in zip(symbols, values):
         final = sp.sympify(final).replace(s, v)
     return final
+
+
+# compiled skeletons, keyed by the token sequence: beams of successive fitfunc calls on the
+# same problem repeat most of their candidates (scripts/*_test.py loop 8x per equation)
+_COMPILED = {}
+_COMPILED_MAX = 8192
+
+
+def _compile_candidate(toks, cfg, test_data, variables):
+    key = (tuple(int(t) for t in (toks.tolist() if hasattr(toks, "tolist") else toks)),
+           bool(_opt(cfg, "add_coefficients_if_not_existing", False)), tuple(variables),
+           test_data.id2word.get(3))
+    hit = _COMPILED.get(key)
+    if hit is None:
+        expr, k = skeleton_string(toks, cfg, test_data)
+        prog = compile_sympy(sp.sympify(expr), k, variables)
+        if len(_COMPILED) >= _COMPILED_MAX:
+            _COMPILED.pop(next(iter(_COMPILED)))
+        hit = _COMPILED[key] = (expr, k, prog)
+    return hit
 
 
 def bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
@@ -122,8 +156,7 @@ def bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
     for toks in pred_strs:
         c = _Candidate()
         try:
-            c.expr, c.k = skeleton_string(toks, cfg, test_data)
-            c.prog = compile_sympy(sp.sympify(c.expr), c.k, variables)
+            c.expr, c.k, c.prog = _compile_candidate(toks, cfg, test_data, variables)
         except Exception as exc:  # noqa: BLE001 -- the wrapper's contract (model.py:15-19)
             c.error = exc
         cands.append(c)
@@ -266,10 +299,10 @@ def bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
         if len(entry) > 3:  # pruned: zeros first, then the re-fitted ones (bfgs.py:184-196)
             order = list(entry[4]) + [i for i in range(c.k) if i not in entry[4]]
             vals = [0.0 if i in entry[4] else best_consts[i] for i in order]
-            final_expr = _substitute(c.expr, [csyms[i] for i in order], vals)
+            final_expr = _substitute(c.prog.expr, [csyms[i] for i in order], vals)
             consts_out = [0.0 if i in entry[4] else best_consts[i] for i in range(c.k)]
         else:
-            final_expr = _substitute(c.expr, csyms, list(best_consts))
+            final_expr = _substitute(c.prog.expr, csyms, list(best_consts))
             consts_out = best_consts
         results[ci] = (str(final_expr), consts_out, best_loss, c.expr)
     return results
