@@ -98,6 +98,7 @@ struct vsr_handle {
   DevBuf d_lists;    // grouped run / pair lists
   DevBuf d_partial;  // eval partial sums
   DevBuf d_stage;    // device staging of the *_host entry points
+  DevBuf d_state;    // optimiser images of paused runs + done flags (budgeted rounds)
   PinnedBuf h_lists;
   int64_t launches = 0;
   // measurement hooks
@@ -248,14 +249,15 @@ struct Geometry {
 };
 
 constexpr int kMaxCluster = 16;              // 16 needs the non-portable cluster size opt-in
+constexpr int kThroughputCluster = 4;        // cluster cap of round 0 (throughput geometry)
 constexpr size_t kSmemBudget = 200 * 1024;  // of the 227 KB a CTA can own; leaves room for static smem
 
 Geometry choose_geometry(int64_t N, int P, int cap_threads, int forced_warps, int kmax, int K, int max_insn,
-                         int max_imm, int max_slots, int elem) {
+                         int max_imm, int max_slots, int elem, int max_cluster) {
   Geometry g;
   const int64_t per_iter = (int64_t)cap_threads * P;
   int cs = 1;
-  while (cs < kMaxCluster && (N + cs - 1) / cs > per_iter) cs <<= 1;
+  while (cs < max_cluster && (N + cs - 1) / cs > per_iter) cs <<= 1;
   int64_t per = (N + cs - 1) / cs;
   per = (per + 31) & ~(int64_t)31;
   int threads = (int)std::min<int64_t>(cap_threads, ((per + P - 1) / P + 31) & ~(int64_t)31);
@@ -403,6 +405,7 @@ void vsr_destroy(vsr_handle* h) {
   h->d_lists.release();
   h->d_partial.release();
   h->d_stage.release();
+  h->d_state.release();
   h->h_lists.release();
   for (auto s2 : h->side_streams) cudaStreamDestroy(s2);
   for (auto e2 : h->ev_join) cudaEventDestroy(e2);
@@ -745,6 +748,43 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     ev_c = take_event(h);
     VSR_CUDA(h, cudaEventRecord(ev_a, st));
   }
+  // ---- budgeted rounds ----
+  // Run lengths are heavy-tailed (most restarts need tens of sweeps, a few hit the 200 k
+  // iteration cap with thousands).  One launch per run would leave the long runs queued behind
+  // short ones and the tail of the launch nearly idle.  So: round 0 gives every run a small
+  // budget of sweeps on SMALL clusters (throughput geometry: less barrier/optimiser idling per
+  // SM); unfinished runs save their optimiser image and are resumed in later rounds on LARGE
+  // clusters (latency geometry: one tile iteration per sweep), all of them starting together.
+  // The geometry depends on (N, round) only, so results do not depend on how runs are sharded.
+  int n_slots_used = 0;
+  for (int r = 0; r < n_runs; ++r) n_slots_used = std::max(n_slots_used, run_slot[r] + 1);
+  int kmax_all = 0;
+  for (auto& g : groups) kmax_all = std::max(kmax_all, g.kmax);
+  const int img_head = (int)((sizeof(vsr::FitState) + 8 + 15) / 16 * 16);
+  const int state_stride = (img_head + 8 * vsr::fit_workspace_doubles(kmax_all) + 15) / 16 * 16;
+  const size_t state_bytes = (size_t)n_slots_used * state_stride;
+  const size_t done_off = (state_bytes + 255) / 256 * 256;
+  VSR_CUDA(h, h->d_state.reserve(done_off + (size_t)n_slots_used * sizeof(int32_t)));
+  unsigned char* d_state = (unsigned char*)h->d_state.p;
+  int32_t* d_done = (int32_t*)(d_state + done_off);
+  VSR_CUDA(h, cudaMemsetAsync(d_done, 0, (size_t)n_slots_used * sizeof(int32_t), st));
+
+  int budgets[3] = {0, 0, 0};
+  int n_rounds = 1;
+  {
+    // rounds pay off when the latency geometry needs big clusters and there are many runs
+    const int cap0 = opts->eval_dtype == VSR_F64 ? fit_threads_cap<double>(groups[0].K) : fit_threads_cap<float>(groups[0].K);
+    const int P0 = points_per_thread(groups[0].K);
+    int cs_lat = 1;
+    while (cs_lat < kMaxCluster && (ps.n + cs_lat - 1) / cs_lat > (int64_t)cap0 * P0) cs_lat <<= 1;
+    if (cs_lat > kThroughputCluster && n_runs >= 128 && opts->warps_per_run == 0) {
+      n_rounds = 3;
+      budgets[0] = 64;
+      budgets[1] = 256;
+      budgets[2] = 0;
+    }
+  }
+
   // groups run concurrently: group 0 on the caller's stream, the others on side streams
   // forked from / joined to it with events
   const size_t n_side = groups.size() > 1 ? groups.size() - 1 : 0;
@@ -756,54 +796,60 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     VSR_CUDA(h, cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
     h->ev_join.push_back(e2);
   }
-  if (n_side) {
-    if (!h->ev_fork) VSR_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    VSR_CUDA(h, cudaEventRecord(h->ev_fork, st));
-  }
-  for (size_t gi = 0; gi < groups.size(); ++gi) {
-    Group& g = groups[gi];
-    const int n = (int)g.prog.size();
-    cudaStream_t gs = gi == 0 ? st : h->side_streams[gi - 1];
-    if (gi > 0) VSR_CUDA(h, cudaStreamWaitEvent(gs, h->ev_fork, 0));
-    vsr::FitArgs a;
-    a.pt = table_of(h);
-    a.pts = points_of(ps);
-    a.run_prog = dl + off[gi];
-    a.run_slot = dl + off[gi] + n;
-    a.n_runs = n;
-    a.kstride = kstride;
-    a.x0 = x0;
-    a.out_consts = out_consts;
-    a.out_lastx = out_lastx;
-    a.out_loss = out_loss;
-    a.out_info = out_info;
-    a.O.gtol = opts->gtol;
-    a.O.c1 = opts->c1;
-    a.O.c2 = opts->c2;
-    a.O.xrtol = opts->xrtol;
-    a.O.fd_eps = opts->fd_eps;
-    a.O.penalty = opts->penalty;
-    a.O.loss_scale = opts->loss_scale;
-    a.O.stop_time = opts->stop_time;
-    a.O.maxiter_per_k = opts->maxiter_per_k;
-    a.O.grad_mode = g.grad_mode;
-    const int P = points_per_thread(g.K);
-    const int cap = opts->eval_dtype == VSR_F64 ? fit_threads_cap<double>(g.K) : fit_threads_cap<float>(g.K);
-    Geometry geo = choose_geometry(g.kmax == 0 ? 1 : ps.n, P, cap, opts->warps_per_run, g.kmax, g.K,
-                                   g.max_insn, g.max_imm, g.max_slots, elem);
-    a.phase_cycles = h->phase_cycles;
-    a.resident = geo.resident;
-    a.tma_ok = tma_ok ? 1 : 0;
-    a.slice_stride = geo.stride;
-    cudaError_t e = opts->eval_dtype == VSR_F64 ? launch_fit<double>(g.K, a, geo.threads, geo.cs, geo.smem, gs)
-                                                : launch_fit<float>(g.K, a, geo.threads, geo.cs, geo.smem, gs);
-    if (e != cudaSuccess)
-      return fail(h, VSR_ECUDA, "fit kernel launch failed (K=%d threads=%d cluster=%d smem=%zu): %s", g.K,
-                  geo.threads, geo.cs, geo.smem, cudaGetErrorString(e));
-    h->launches += 1;
-    if (gi > 0) {
-      VSR_CUDA(h, cudaEventRecord(h->ev_join[gi - 1], gs));
-      VSR_CUDA(h, cudaStreamWaitEvent(st, h->ev_join[gi - 1], 0));
+  if (n_side && !h->ev_fork) VSR_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  for (int round = 0; round < n_rounds; ++round) {
+    if (n_side) VSR_CUDA(h, cudaEventRecord(h->ev_fork, st));
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+      Group& g = groups[gi];
+      const int n = (int)g.prog.size();
+      cudaStream_t gs = gi == 0 ? st : h->side_streams[gi - 1];
+      if (gi > 0) VSR_CUDA(h, cudaStreamWaitEvent(gs, h->ev_fork, 0));
+      vsr::FitArgs a;
+      a.pt = table_of(h);
+      a.pts = points_of(ps);
+      a.run_prog = dl + off[gi];
+      a.run_slot = dl + off[gi] + n;
+      a.n_runs = n;
+      a.kstride = kstride;
+      a.x0 = x0;
+      a.out_consts = out_consts;
+      a.out_lastx = out_lastx;
+      a.out_loss = out_loss;
+      a.out_info = out_info;
+      a.O.gtol = opts->gtol;
+      a.O.c1 = opts->c1;
+      a.O.c2 = opts->c2;
+      a.O.xrtol = opts->xrtol;
+      a.O.fd_eps = opts->fd_eps;
+      a.O.penalty = opts->penalty;
+      a.O.loss_scale = opts->loss_scale;
+      a.O.stop_time = opts->stop_time;
+      a.O.maxiter_per_k = opts->maxiter_per_k;
+      a.O.grad_mode = g.grad_mode;
+      const int P = points_per_thread(g.K);
+      const int cap = opts->eval_dtype == VSR_F64 ? fit_threads_cap<double>(g.K) : fit_threads_cap<float>(g.K);
+      const int max_cluster = (n_rounds > 1 && round == 0) ? kThroughputCluster : kMaxCluster;
+      Geometry geo = choose_geometry(g.kmax == 0 ? 1 : ps.n, P, cap, opts->warps_per_run, g.kmax, g.K,
+                                     g.max_insn, g.max_imm, g.max_slots, elem, max_cluster);
+      a.phase_cycles = h->phase_cycles;
+      a.resident = geo.resident;
+      a.tma_ok = tma_ok ? 1 : 0;
+      a.slice_stride = geo.stride;
+      a.state = d_state;
+      a.run_done = d_done;
+      a.state_stride = state_stride;
+      a.max_passes = budgets[round];
+      a.resume = round > 0 ? 1 : 0;
+      cudaError_t e = opts->eval_dtype == VSR_F64 ? launch_fit<double>(g.K, a, geo.threads, geo.cs, geo.smem, gs)
+                                                  : launch_fit<float>(g.K, a, geo.threads, geo.cs, geo.smem, gs);
+      if (e != cudaSuccess)
+        return fail(h, VSR_ECUDA, "fit kernel launch failed (K=%d threads=%d cluster=%d smem=%zu): %s", g.K,
+                    geo.threads, geo.cs, geo.smem, cudaGetErrorString(e));
+      h->launches += 1;
+      if (gi > 0) {
+        VSR_CUDA(h, cudaEventRecord(h->ev_join[gi - 1], gs));
+        VSR_CUDA(h, cudaStreamWaitEvent(st, h->ev_join[gi - 1], 0));
+      }
     }
   }
   if (h->profiling) VSR_CUDA(h, cudaEventRecord(ev_b, st));
@@ -813,7 +859,7 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
                       out_final_mse, nullptr, st);
   if (h->profiling) {
     VSR_CUDA(h, cudaEventRecord(ev_c, st));
-    h->spans.push_back({ev_a, ev_b, 0, (int)groups.size()});
+    h->spans.push_back({ev_a, ev_b, 0, (int)groups.size() * n_rounds});
     h->spans.push_back({ev_b, ev_c, 1, 2});
   }
   return rc;

@@ -59,6 +59,14 @@ struct FitArgs {
   int32_t tma_ok;        // 1: column starts and strides are 16-byte aligned (bulk copies)
   int32_t slice_stride;  // elements between columns of the staged slice
   long long* phase_cycles;  // optional [n_slots][8]: SM cycles per phase of the pass loop (leader thread 0)
+  // budgeted rounds: a run that has not finished after `max_passes` sweeps of this launch saves
+  // its optimiser image and exits; the next launch resumes it (resume = 1).  Finished runs are
+  // flagged in run_done and their clusters exit at once.
+  unsigned char* state;     // [n_slots][state_stride] bytes: FitState image | timer | workspace
+  int32_t* run_done;        // [n_slots]
+  int32_t state_stride;
+  int32_t max_passes;       // <= 0: unlimited
+  int32_t resume;
   FitOpts O;
 };
 
@@ -332,6 +340,7 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   double* red = cred + cs * (K + 1);
   T* cst = reinterpret_cast<T*>(red + nw * (K + 1));
   double* s_imm = red + nw * (K + 1) + k + 1;
+  if (a.resume && a.run_done[slot]) return;  // finished in an earlier round; uniform over the cluster
   int n_insn, n_imm;
   const int m_imm = a.pt.imm_off[prog + 1] - a.pt.imm_off[prog];
   vsr_insn_t* s_insn = reinterpret_cast<vsr_insn_t*>(s_imm + m_imm);
@@ -345,6 +354,7 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
       info[2] = 0;
       info[3] = 0;
       a.out_loss[slot] = 0.0;
+      if (a.run_done) a.run_done[slot] = 1;
     }
     return;
   }
@@ -418,9 +428,23 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   __syncthreads();
 
   const bool is_logic = crank == 0 && tid < 32;  // warp 0 of the leader: the optimiser
+  unsigned char* image = a.state ? a.state + (int64_t)slot * a.state_stride : nullptr;
+  constexpr int kImgHead = (int)((sizeof(FitState) + 8 + 15) / 16 * 16);  // FitState | s_t0, 16-aligned
   if (is_logic) {
-    fit_init(S, k, ws, a.x0 + (int64_t)slot * a.kstride);
-    if (tid == 0) s_t0 = 0ull;
+    if (a.resume) {
+      // every lane takes its own copy of the saved scalar state, the vectors go back to
+      // shared memory, and the pending evaluation request (S.xe) is served first
+      const FitState* saved = reinterpret_cast<const FitState*>(image);
+      S = *saved;
+      fit_rebase(S, k, ws);
+      const double* wsg = reinterpret_cast<const double*>(image + kImgHead);
+      for (int i = tid; i < fit_workspace_doubles(k); i += 32) ws[i] = wsg[i];
+      if (tid == 0) s_t0 = *reinterpret_cast<const unsigned long long*>(image + sizeof(FitState));
+      __syncwarp();
+    } else {
+      fit_init(S, k, ws, a.x0 + (int64_t)slot * a.kstride);
+      if (tid == 0) s_t0 = 0ull;
+    }
   }
   // leader state is initialised and every CTA of the cluster is running before any DSMEM access
   cluster.sync();
@@ -443,15 +467,31 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
     tprev = tn;                      \
   }
 
+  int passes = 0;
+  bool pending = a.resume != 0;  // a resumed run re-enters at its saved evaluation request
   for (;;) {
     if (is_logic) {
-      const int act = fit_step_call(S, a.O);
+      int act = VSR_NEED_EVAL;
+      if (!pending) act = fit_step_call(S, a.O);
+      if (act == VSR_NEED_EVAL && a.max_passes > 0 && passes >= a.max_passes) {
+        // budget of this round used up: save the image, stop here (the request stays pending)
+        act = VSR_PAUSE;
+        __syncwarp();
+        if (tid == 0) {
+          *reinterpret_cast<FitState*>(image) = S;
+          *reinterpret_cast<unsigned long long*>(image + sizeof(FitState)) = s_t0;
+        }
+        double* wsg = reinterpret_cast<double*>(image + kImgHead);
+        for (int i = tid; i < fit_workspace_doubles(k); i += 32) wsg[i] = ws[i];
+      }
       if (tid == 0) s_action = act;
     }
+    pending = false;
+    ++passes;
     VSR_PHASE(0)
     cluster.sync();
     VSR_PHASE(1)
-    if (*r_action == VSR_DONE) break;
+    if (*r_action != VSR_NEED_EVAL) break;
     // trial constants from the leader, in the arithmetic type of the sweep
     for (int i = tid; i < k; i += blockDim.x) cst[i] = (T)r_xe[i];
     __syncthreads();
@@ -507,9 +547,10 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   }
 #undef VSR_PHASE
   if (timing)
-    for (int i = 0; i < 8; ++i) a.phase_cycles[(int64_t)slot * 8 + i] = ph[i];
+    for (int i = 0; i < 8; ++i) a.phase_cycles[(int64_t)slot * 8 + i] += ph[i];
 
-  if (crank == 0 && tid == 0) {
+  if (crank == 0 && tid == 0 && s_action == VSR_DONE) {
+    if (a.run_done) a.run_done[slot] = 1;
     double* oc = a.out_consts + (int64_t)slot * a.kstride;
     double* ol = a.out_lastx + (int64_t)slot * a.kstride;
     for (int i = 0; i < k; ++i) {
