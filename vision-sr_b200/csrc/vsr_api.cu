@@ -3,12 +3,14 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/vsr.h"
-#include "vsr_kernels.cuh"
+#define VSR_API_TU 1
+#include "vsr_launch.h"
 
 namespace {
 
@@ -165,39 +167,14 @@ vsr::Points points_of(const PointSlot& s) {
   return p;
 }
 
-// points per thread for a tangent width: wide duals are register hungry
-constexpr int points_per_thread(int K) { return K <= 8 ? 2 : 1; }
+using vsr::points_per_thread;
 
-template <typename T, int K>
-cudaError_t launch_fit_T(const vsr::FitArgs& a, int threads, int cs, size_t smem, cudaStream_t st) {
-  constexpr int P = points_per_thread(K);
-  auto kern = vsr::fit_kernel<T, K, P>;
-  if (threads > vsr::fit_max_threads<T, K>()) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
-  if (e != cudaSuccess) return e;
-  if (cs > 8) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return e;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)a.n_runs * cs);
-  cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, a);
-}
-
+// the kernels are instantiated one (type, width) pair per translation unit (vsr_inst.cu) so the
+// library builds in parallel; here only the dispatch over the runtime width
 template <typename T>
 cudaError_t launch_fit(int K, const vsr::FitArgs& a, int threads, int cs, size_t smem, cudaStream_t st) {
   switch (K) {
-#define C(KK) case KK: return launch_fit_T<T, KK>(a, threads, cs, smem, st);
+#define C(KK) case KK: return vsr::launch_fit_T<T, KK>(a, threads, cs, smem, st);
     C(0) C(1) C(2) C(3) C(4) C(6) C(8) C(12) C(16)
 #undef C
   }
@@ -214,19 +191,10 @@ int fit_threads_cap(int K) {
   return 256;
 }
 
-template <typename T, int K>
-cudaError_t launch_eval_T(const vsr::EvalArgs& a, int threads, size_t smem, cudaStream_t st) {
-  constexpr int P = points_per_thread(K);
-  auto kern = vsr::eval_kernel<T, K, P>;
-  dim3 grid(a.n_pairs, a.nsplit);
-  kern<<<grid, threads, smem, st>>>(a);
-  return cudaGetLastError();
-}
-
 template <typename T>
 cudaError_t launch_eval(int K, const vsr::EvalArgs& a, int threads, size_t smem, cudaStream_t st) {
   switch (K) {
-#define C(KK) case KK: return launch_eval_T<T, KK>(a, threads, smem, st);
+#define C(KK) case KK: return vsr::launch_eval_T<T, KK>(a, threads, smem, st);
     C(0) C(1) C(2) C(3) C(4) C(6) C(8) C(12) C(16)
 #undef C
   }
@@ -249,7 +217,7 @@ struct Geometry {
 };
 
 constexpr int kMaxCluster = 16;              // 16 needs the non-portable cluster size opt-in
-constexpr int kThroughputCluster = 4;        // cluster cap of round 0 (throughput geometry)
+constexpr int kDefaultThreads = 160;          // widest CTA of the default plan (see vsr_fit)
 constexpr size_t kSmemBudget = 200 * 1024;  // of the 227 KB a CTA can own; leaves room for static smem
 
 Geometry choose_geometry(int64_t N, int P, int cap_threads, int forced_warps, int kmax, int K, int max_insn,
@@ -769,19 +737,42 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
   int32_t* d_done = (int32_t*)(d_state + done_off);
   VSR_CUDA(h, cudaMemsetAsync(d_done, 0, (size_t)n_slots_used * sizeof(int32_t), st));
 
-  int budgets[3] = {0, 0, 0};
+  constexpr int kMaxRounds = 6;
+  int budgets[kMaxRounds] = {0};
+  int round_cluster[kMaxRounds] = {kMaxCluster};
+  int round_threads[kMaxRounds] = {0};  // 0: the kernel's widest CTA
   int n_rounds = 1;
   {
-    // rounds pay off when the latency geometry needs big clusters and there are many runs
-    const int cap0 = opts->eval_dtype == VSR_F64 ? fit_threads_cap<double>(groups[0].K) : fit_threads_cap<float>(groups[0].K);
-    const int P0 = points_per_thread(groups[0].K);
-    int cs_lat = 1;
-    while (cs_lat < kMaxCluster && (ps.n + cs_lat - 1) / cs_lat > (int64_t)cap0 * P0) cs_lat <<= 1;
-    if (cs_lat > kThroughputCluster && n_runs >= 128 && opts->warps_per_run == 0) {
-      n_rounds = 3;
-      budgets[0] = 64;
-      budgets[1] = 256;
-      budgets[2] = 0;
+    // Default plan: ONE round, clusters of up to 16 CTAs of at most 160 threads.  Measured on the
+    // BASELINE config-2 beams (tools/exp_schedules.py, 27 beams): 16 x 160 threads 1727 ms,
+    // 8 x 320 1672 ms, 16 x 320 (one tile iteration per sweep) 2201 ms, and every multi-round plan
+    // (short first round on small clusters, tail resumed on big ones) 1840-2340 ms.  Four small
+    // CTAs of four different runs per SM overlap one run's optimiser step and cluster barriers
+    // with the other runs' sweeps; re-staging the slices and relaunching costs more than the
+    // rounds save.  The rounds stay available through VSR_SCHEDULE.
+    round_threads[0] = kDefaultThreads;
+    // measurement hook: VSR_SCHEDULE="cluster:budget[:threads],..." overrides the round plan
+    if (const char* env = getenv("VSR_SCHEDULE")) {
+      int n = 0;
+      const char* q = env;
+      while (*q && n < kMaxRounds) {
+        int c = 0, b = 0, t = 0, used = 0;
+        if (sscanf(q, "%d:%d%n", &c, &b, &used) < 2) break;
+        q += used;
+        if (*q == ':') {
+          int u2 = 0;
+          if (sscanf(q + 1, "%d%n", &t, &u2) == 1) q += 1 + u2;
+        }
+        round_cluster[n] = std::max(1, std::min(c, kMaxCluster));
+        budgets[n] = b;
+        round_threads[n] = t > 0 ? std::max(32, t & ~31) : 0;  // whole warps
+        ++n;
+        if (*q == ',') ++q;
+      }
+      if (n > 0) {
+        n_rounds = n;
+        budgets[n - 1] = 0;  // the last round runs everything out
+      }
     }
   }
 
@@ -828,8 +819,9 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
       a.O.grad_mode = g.grad_mode;
       const int P = points_per_thread(g.K);
       const int cap = opts->eval_dtype == VSR_F64 ? fit_threads_cap<double>(g.K) : fit_threads_cap<float>(g.K);
-      const int max_cluster = (n_rounds > 1 && round == 0) ? kThroughputCluster : kMaxCluster;
-      Geometry geo = choose_geometry(g.kmax == 0 ? 1 : ps.n, P, cap, opts->warps_per_run, g.kmax, g.K,
+      const int max_cluster = round_cluster[round];
+      const int cap_r = round_threads[round] > 0 ? std::min(cap, round_threads[round]) : cap;
+      Geometry geo = choose_geometry(g.kmax == 0 ? 1 : ps.n, P, cap_r, opts->warps_per_run, g.kmax, g.K,
                                      g.max_insn, g.max_imm, g.max_slots, elem, max_cluster);
       a.phase_cycles = h->phase_cycles;
       a.resident = geo.resident;

@@ -1,0 +1,48 @@
+// vsr_inst.cu -- one instantiation of fit_kernel / eval_kernel and their launch wrappers:
+// compiled once per (VSR_INST_T, VSR_INST_K) pair, see the Makefile.
+#include <algorithm>
+
+#include "vsr_launch.h"
+
+namespace vsr {
+
+template <typename T, int K>
+cudaError_t launch_fit_T(const FitArgs& a, int threads, int cs, size_t smem, cudaStream_t st) {
+  constexpr int P = points_per_thread(K);
+  auto kern = fit_kernel<T, K, P>;
+  if (threads > fit_max_threads<T, K>()) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)std::max<size_t>(smem, 1024));
+  if (e != cudaSuccess) return e;
+  if (cs > 8) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)a.n_runs * cs);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+template <typename T, int K>
+cudaError_t launch_eval_T(const EvalArgs& a, int threads, size_t smem, cudaStream_t st) {
+  constexpr int P = points_per_thread(K);
+  auto kern = eval_kernel<T, K, P>;
+  dim3 grid(a.n_pairs, a.nsplit);
+  kern<<<grid, threads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template cudaError_t launch_fit_T<VSR_INST_T, VSR_INST_K>(const FitArgs&, int, int, size_t, cudaStream_t);
+template cudaError_t launch_eval_T<VSR_INST_T, VSR_INST_K>(const EvalArgs&, int, size_t, cudaStream_t);
+
+}  // namespace vsr

@@ -27,7 +27,7 @@
 // the heavy libm routines are kept OUT of line: the interpreter has ~60 handlers and P
 // copies of each; inlining pow/sin/... into all of them made the kernels 300-500 KB of
 // SASS, far beyond the instruction caches.  One copy per kernel, reached by a call.
-#define VSR_MATH __host__ __device__ __noinline__
+#define VSR_MATH __host__ __device__ __noinline__ inline
 #else
 #include <cmath>
 #define VSR_HD inline

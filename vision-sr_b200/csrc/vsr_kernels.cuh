@@ -312,7 +312,7 @@ __host__ __device__ constexpr int fit_min_ctas() {
 
 // The optimiser step, out of line: its register and stack needs stay out of the sweep's
 // allocation (the sweep is the hot loop; this runs on one warp between sweeps).
-__device__ __noinline__ int fit_step_call(FitState& S, const FitOpts& O) { return fit_step(S, O); }
+static __device__ __noinline__ int fit_step_call(FitState& S, const FitOpts& O) { return fit_step(S, O); }
 
 template <typename T, int K, int P>
 __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>())) fit_kernel(const FitArgs a) {
@@ -613,6 +613,7 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalArgs a) {
   }
 }
 
+#if defined(VSR_API_TU)  // plain kernels: defined once, in the API translation unit
 // out_loss[row] = sum_splits partial / N ; out_grad[row][t] = 2 * sum / N  (t < k, else 0)
 __global__ void eval_finalize(const double* partial, const int32_t* pair_prog,
                               const int32_t* pair_out, const int32_t* prog_k, int n_pairs,
@@ -640,6 +641,8 @@ __global__ void fill_nan_rows(const int32_t* rows, int n_rows, int kstride, doub
   if (idx >= n_rows * kstride) return;
   out[(int64_t)rows[idx / kstride] * kstride + idx % kstride] = __longlong_as_double(0x7ff8000000000000ll);
 }
+
+#endif  // VSR_API_TU
 
 }  // namespace vsr
 

@@ -65,7 +65,7 @@ def build(force=False, verbose=False):
     """Compile libvsr.so for sm_100a with nvcc (cross-compiles without a GPU)."""
     if force and os.path.exists(LIB_PATH):
         os.remove(LIB_PATH)
-    cmd = ["make", "-C", isa.CSRC_DIR, "libvsr.so"]
+    cmd = ["make", "-j", str(os.cpu_count() or 4), "-C", isa.CSRC_DIR, "libvsr.so"]
     out = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         print(out.stdout, out.stderr)
