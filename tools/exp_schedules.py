@@ -1,4 +1,4 @@
-"""GPU probe: step time of the bench beams under different round plans (VSR_SCHEDULE hook).
+"""GPU probe: step time of the bench beams under different launch geometries (VSR_GEOMETRY="cluster:threads:seats" hook).
 usage: python tools/exp_schedules.py N_BEAMS "sched1" "sched2" ...   ("" = built-in plan)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -21,8 +21,8 @@ for b in beams:
     setups.append((eng, torch.from_numpy(x0).to(dev), np.repeat(np.arange(C), R), np.arange(C * R)))
 ref = None
 for sc in scheds:
-    if sc: os.environ["VSR_SCHEDULE"] = sc
-    else: os.environ.pop("VSR_SCHEDULE", None)
+    if sc: os.environ["VSR_GEOMETRY"] = sc
+    else: os.environ.pop("VSR_GEOMETRY", None)
     ms = []
     losses = []
     for rep in range(2):

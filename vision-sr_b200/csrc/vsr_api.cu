@@ -92,6 +92,7 @@ struct vsr_handle {
   // programs
   DevBuf d_insns, d_insn_off, d_imms, d_imm_off, d_k;
   std::vector<int32_t> h_k, h_ninsn, h_nimm, h_nvars;
+  std::vector<uint32_t> h_varmask;
   std::vector<cudaStream_t> side_streams;
   cudaEvent_t ev_fork = nullptr;
   std::vector<cudaEvent_t> ev_join;
@@ -100,7 +101,7 @@ struct vsr_handle {
   DevBuf d_lists;    // grouped run / pair lists
   DevBuf d_partial;  // eval partial sums
   DevBuf d_stage;    // device staging of the *_host entry points
-  DevBuf d_state;    // optimiser images of paused runs + done flags (budgeted rounds)
+  DevBuf d_queue;    // one run counter per launch group (persistent clusters pull runs from it)
   PinnedBuf h_lists;
   int64_t launches = 0;
   // measurement hooks
@@ -172,9 +173,9 @@ using vsr::points_per_thread;
 // the kernels are instantiated one (type, width) pair per translation unit (vsr_inst.cu) so the
 // library builds in parallel; here only the dispatch over the runtime width
 template <typename T>
-cudaError_t launch_fit(int K, const vsr::FitArgs& a, int threads, int cs, size_t smem, cudaStream_t st) {
+cudaError_t launch_fit(int K, const vsr::FitArgs& a, int threads, int cs, size_t smem, int clusters, cudaStream_t st) {
   switch (K) {
-#define C(KK) case KK: return vsr::launch_fit_T<T, KK>(a, threads, cs, smem, st);
+#define C(KK) case KK: return vsr::launch_fit_T<T, KK>(a, threads, cs, smem, clusters, st);
     C(0) C(1) C(2) C(3) C(4) C(6) C(8) C(12) C(16)
 #undef C
   }
@@ -207,21 +208,22 @@ int next_pow2(int64_t v) {
   return p;
 }
 
-// Geometry of one run: a cluster of `cs` CTAs of `threads` threads, each CTA owning a
-// contiguous slice of `stride` points.  Aim: a pass over the points is one or two tile
-// iterations per thread (the optimiser's critical path is passes x latency per pass), and
-// the slice fits the CTA's shared memory so the points are read from HBM once per run.
+// Geometry of a launch: persistent clusters of `cs` CTAs of `threads` threads, each cluster
+// working on `seats` runs at a time, each CTA owning a contiguous slice of `stride` points.
+// Aim: a sweep over the points is one or two tile iterations per thread (the critical path of a
+// long run is passes x latency per pass), and the slice fits the CTA's shared memory so the
+// points are read from HBM once per cluster.
 struct Geometry {
-  int cs, threads, stride, resident;
+  int cs, threads, stride, resident, seats;
   size_t smem;
 };
 
-constexpr int kMaxCluster = 16;              // 16 needs the non-portable cluster size opt-in
-constexpr int kDefaultThreads = 160;          // widest CTA of the default plan (see vsr_fit)
-constexpr size_t kSmemBudget = 200 * 1024;  // of the 227 KB a CTA can own; leaves room for static smem
+constexpr int kMaxCluster = 16;             // 16 needs the non-portable cluster size opt-in
+constexpr int kDefaultSeats = 4;            // runs in flight per cluster
+constexpr size_t kSmemBudget = 100 * 1024;  // per CTA: two CTAs per SM keep their slices resident
 
 Geometry choose_geometry(int64_t N, int P, int cap_threads, int forced_warps, int kmax, int K, int max_insn,
-                         int max_imm, int max_slots, int elem, int max_cluster) {
+                         int max_imm, int n_cols, int elem, int max_cluster, int seats) {
   Geometry g;
   const int64_t per_iter = (int64_t)cap_threads * P;
   int cs = 1;
@@ -234,9 +236,10 @@ Geometry choose_geometry(int64_t N, int P, int cap_threads, int forced_warps, in
   g.cs = cs;
   g.threads = threads;
   g.stride = (int)per;
-  const size_t with = vsr::fit_smem_bytes(kmax, K, threads / 32, cs, max_insn, max_imm, max_slots, (int)per, elem);
+  g.seats = std::max(1, std::min(std::min(seats, threads / 32), (int)vsr::kMaxSeats));
+  const size_t with = vsr::fit_smem_bytes(g.seats, kmax, K, threads / 32, cs, max_insn, max_imm, n_cols, (int)per, elem);
   g.resident = with <= kSmemBudget && per < (1 << 30);
-  g.smem = g.resident ? with : vsr::fit_smem_bytes(kmax, K, threads / 32, cs, max_insn, max_imm, -1, 0, elem);
+  g.smem = g.resident ? with : vsr::fit_smem_bytes(g.seats, kmax, K, threads / 32, cs, max_insn, max_imm, -1, 0, elem);
   return g;
 }
 
@@ -244,7 +247,8 @@ struct Group {
   int K;
   int grad_mode;
   std::vector<int32_t> prog, slot;
-  int kmax = 0, max_insn = 0, max_imm = 0, max_slots = 0;
+  int kmax = 0, max_insn = 0, max_imm = 0;
+  unsigned var_mask = 0;  // variables any of the group's programs reads
 };
 
 // copies host int32 lists into the handle's device list buffer at `offset` (in ints)
@@ -373,7 +377,7 @@ void vsr_destroy(vsr_handle* h) {
   h->d_lists.release();
   h->d_partial.release();
   h->d_stage.release();
-  h->d_state.release();
+  h->d_queue.release();
   h->h_lists.release();
   for (auto s2 : h->side_streams) cudaStreamDestroy(s2);
   for (auto e2 : h->ev_join) cudaEventDestroy(e2);
@@ -477,6 +481,7 @@ int vsr_upload_programs(vsr_handle* h, const uint64_t* insns, const int32_t* ins
   h->h_ninsn.resize(n_programs);
   h->h_nimm.resize(n_programs);
   h->h_nvars.assign(n_programs, 0);
+  h->h_varmask.assign(n_programs, 0u);
   for (int c = 0; c < n_programs; ++c) {
     const int ni = insn_off[c + 1] - insn_off[c];
     const int nm = imm_off[c + 1] - imm_off[c];
@@ -509,6 +514,7 @@ int vsr_upload_programs(vsr_handle* h, const uint64_t* insns, const int32_t* ins
     h->h_ninsn[c] = ni;
     h->h_nimm[c] = nm;
     h->h_nvars[c] = __builtin_popcount(var_mask);
+    h->h_varmask[c] = var_mask;
   }
   const size_t nins = insn_off[n_programs], nimm = std::max(1, imm_off[n_programs]);
   VSR_CUDA(h, h->d_insns.reserve(nins * sizeof(uint64_t)));
@@ -662,7 +668,7 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     g.kmax = std::max(g.kmax, k);
     g.max_insn = std::max(g.max_insn, h->h_ninsn[c]);
     g.max_imm = std::max(g.max_imm, h->h_nimm[c]);
-    g.max_slots = std::max(g.max_slots, h->h_nvars[c]);
+    g.var_mask |= h->h_varmask[c];
   }
   // widest groups first: their runs have the highest iteration caps (200 k)
   std::stable_sort(groups.begin(), groups.end(), [](const Group& x, const Group& y) { return x.kmax > y.kmax; });
@@ -716,65 +722,12 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     ev_c = take_event(h);
     VSR_CUDA(h, cudaEventRecord(ev_a, st));
   }
-  // ---- budgeted rounds ----
-  // Run lengths are heavy-tailed (most restarts need tens of sweeps, a few hit the 200 k
-  // iteration cap with thousands).  One launch per run would leave the long runs queued behind
-  // short ones and the tail of the launch nearly idle.  So: round 0 gives every run a small
-  // budget of sweeps on SMALL clusters (throughput geometry: less barrier/optimiser idling per
-  // SM); unfinished runs save their optimiser image and are resumed in later rounds on LARGE
-  // clusters (latency geometry: one tile iteration per sweep), all of them starting together.
-  // The geometry depends on (N, round) only, so results do not depend on how runs are sharded.
-  int n_slots_used = 0;
-  for (int r = 0; r < n_runs; ++r) n_slots_used = std::max(n_slots_used, run_slot[r] + 1);
-  int kmax_all = 0;
-  for (auto& g : groups) kmax_all = std::max(kmax_all, g.kmax);
-  const int img_head = (int)((sizeof(vsr::FitState) + 8 + 15) / 16 * 16);
-  const int state_stride = (img_head + 8 * vsr::fit_workspace_doubles(kmax_all) + 15) / 16 * 16;
-  const size_t state_bytes = (size_t)n_slots_used * state_stride;
-  const size_t done_off = (state_bytes + 255) / 256 * 256;
-  VSR_CUDA(h, h->d_state.reserve(done_off + (size_t)n_slots_used * sizeof(int32_t)));
-  unsigned char* d_state = (unsigned char*)h->d_state.p;
-  int32_t* d_done = (int32_t*)(d_state + done_off);
-  VSR_CUDA(h, cudaMemsetAsync(d_done, 0, (size_t)n_slots_used * sizeof(int32_t), st));
-
-  constexpr int kMaxRounds = 6;
-  int budgets[kMaxRounds] = {0};
-  int round_cluster[kMaxRounds] = {kMaxCluster};
-  int round_threads[kMaxRounds] = {0};  // 0: the kernel's widest CTA
-  int n_rounds = 1;
-  {
-    // Default plan: ONE round, clusters of up to 16 CTAs of at most 160 threads.  Measured on the
-    // BASELINE config-2 beams (tools/exp_schedules.py, 27 beams): 16 x 160 threads 1727 ms,
-    // 8 x 320 1672 ms, 16 x 320 (one tile iteration per sweep) 2201 ms, and every multi-round plan
-    // (short first round on small clusters, tail resumed on big ones) 1840-2340 ms.  Four small
-    // CTAs of four different runs per SM overlap one run's optimiser step and cluster barriers
-    // with the other runs' sweeps; re-staging the slices and relaunching costs more than the
-    // rounds save.  The rounds stay available through VSR_SCHEDULE.
-    round_threads[0] = kDefaultThreads;
-    // measurement hook: VSR_SCHEDULE="cluster:budget[:threads],..." overrides the round plan
-    if (const char* env = getenv("VSR_SCHEDULE")) {
-      int n = 0;
-      const char* q = env;
-      while (*q && n < kMaxRounds) {
-        int c = 0, b = 0, t = 0, used = 0;
-        if (sscanf(q, "%d:%d%n", &c, &b, &used) < 2) break;
-        q += used;
-        if (*q == ':') {
-          int u2 = 0;
-          if (sscanf(q + 1, "%d%n", &t, &u2) == 1) q += 1 + u2;
-        }
-        round_cluster[n] = std::max(1, std::min(c, kMaxCluster));
-        budgets[n] = b;
-        round_threads[n] = t > 0 ? std::max(32, t & ~31) : 0;  // whole warps
-        ++n;
-        if (*q == ',') ++q;
-      }
-      if (n > 0) {
-        n_rounds = n;
-        budgets[n - 1] = 0;  // the last round runs everything out
-      }
-    }
-  }
+  // one run counter per group: the persistent clusters of a launch pull their runs from it
+  VSR_CUDA(h, h->d_queue.reserve(groups.size() * sizeof(int32_t)));
+  VSR_CUDA(h, cudaMemsetAsync(h->d_queue.p, 0, groups.size() * sizeof(int32_t), st));
+  // measurement hook: VSR_GEOMETRY="cluster:threads:seats" overrides the launch geometry
+  int hook_cluster = 0, hook_threads = 0, hook_seats = 0;
+  if (const char* env = getenv("VSR_GEOMETRY")) sscanf(env, "%d:%d:%d", &hook_cluster, &hook_threads, &hook_seats);
 
   // groups run concurrently: group 0 on the caller's stream, the others on side streams
   // forked from / joined to it with events
@@ -788,60 +741,67 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     h->ev_join.push_back(e2);
   }
   if (n_side && !h->ev_fork) VSR_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-  for (int round = 0; round < n_rounds; ++round) {
-    if (n_side) VSR_CUDA(h, cudaEventRecord(h->ev_fork, st));
-    for (size_t gi = 0; gi < groups.size(); ++gi) {
-      Group& g = groups[gi];
-      const int n = (int)g.prog.size();
-      cudaStream_t gs = gi == 0 ? st : h->side_streams[gi - 1];
-      if (gi > 0) VSR_CUDA(h, cudaStreamWaitEvent(gs, h->ev_fork, 0));
-      vsr::FitArgs a;
-      a.pt = table_of(h);
-      a.pts = points_of(ps);
-      a.run_prog = dl + off[gi];
-      a.run_slot = dl + off[gi] + n;
-      a.n_runs = n;
-      a.kstride = kstride;
-      a.x0 = x0;
-      a.out_consts = out_consts;
-      a.out_lastx = out_lastx;
-      a.out_loss = out_loss;
-      a.out_info = out_info;
-      a.O.gtol = opts->gtol;
-      a.O.c1 = opts->c1;
-      a.O.c2 = opts->c2;
-      a.O.xrtol = opts->xrtol;
-      a.O.fd_eps = opts->fd_eps;
-      a.O.penalty = opts->penalty;
-      a.O.loss_scale = opts->loss_scale;
-      a.O.stop_time = opts->stop_time;
-      a.O.maxiter_per_k = opts->maxiter_per_k;
-      a.O.grad_mode = g.grad_mode;
-      const int P = points_per_thread(g.K);
-      const int cap = opts->eval_dtype == VSR_F64 ? fit_threads_cap<double>(g.K) : fit_threads_cap<float>(g.K);
-      const int max_cluster = round_cluster[round];
-      const int cap_r = round_threads[round] > 0 ? std::min(cap, round_threads[round]) : cap;
-      Geometry geo = choose_geometry(g.kmax == 0 ? 1 : ps.n, P, cap_r, opts->warps_per_run, g.kmax, g.K,
-                                     g.max_insn, g.max_imm, g.max_slots, elem, max_cluster);
-      a.phase_cycles = h->phase_cycles;
-      a.resident = geo.resident;
-      a.tma_ok = tma_ok ? 1 : 0;
-      a.slice_stride = geo.stride;
-      a.state = d_state;
-      a.run_done = d_done;
-      a.state_stride = state_stride;
-      a.max_passes = budgets[round];
-      a.resume = round > 0 ? 1 : 0;
-      cudaError_t e = opts->eval_dtype == VSR_F64 ? launch_fit<double>(g.K, a, geo.threads, geo.cs, geo.smem, gs)
-                                                  : launch_fit<float>(g.K, a, geo.threads, geo.cs, geo.smem, gs);
-      if (e != cudaSuccess)
-        return fail(h, VSR_ECUDA, "fit kernel launch failed (K=%d threads=%d cluster=%d smem=%zu): %s", g.K,
-                    geo.threads, geo.cs, geo.smem, cudaGetErrorString(e));
-      h->launches += 1;
-      if (gi > 0) {
-        VSR_CUDA(h, cudaEventRecord(h->ev_join[gi - 1], gs));
-        VSR_CUDA(h, cudaStreamWaitEvent(st, h->ev_join[gi - 1], 0));
-      }
+  if (n_side) VSR_CUDA(h, cudaEventRecord(h->ev_fork, st));
+  for (size_t gi = 0; gi < groups.size(); ++gi) {
+    Group& g = groups[gi];
+    const int n = (int)g.prog.size();
+    cudaStream_t gs = gi == 0 ? st : h->side_streams[gi - 1];
+    if (gi > 0) VSR_CUDA(h, cudaStreamWaitEvent(gs, h->ev_fork, 0));
+    vsr::FitArgs a;
+    a.pt = table_of(h);
+    a.pts = points_of(ps);
+    a.run_prog = dl + off[gi];
+    a.run_slot = dl + off[gi] + n;
+    a.n_runs = n;
+    a.kstride = kstride;
+    a.x0 = x0;
+    a.out_consts = out_consts;
+    a.out_lastx = out_lastx;
+    a.out_loss = out_loss;
+    a.out_info = out_info;
+    a.O.gtol = opts->gtol;
+    a.O.c1 = opts->c1;
+    a.O.c2 = opts->c2;
+    a.O.xrtol = opts->xrtol;
+    a.O.fd_eps = opts->fd_eps;
+    a.O.penalty = opts->penalty;
+    a.O.loss_scale = opts->loss_scale;
+    a.O.stop_time = opts->stop_time;
+    a.O.maxiter_per_k = opts->maxiter_per_k;
+    a.O.grad_mode = g.grad_mode;
+    const int P = points_per_thread(g.K);
+    int cap = opts->eval_dtype == VSR_F64 ? fit_threads_cap<double>(g.K) : fit_threads_cap<float>(g.K);
+    if (hook_threads > 0) cap = std::min(cap, std::max(32, hook_threads & ~31));
+    const int max_cluster = hook_cluster > 0 ? std::min(hook_cluster, kMaxCluster) : kMaxCluster;
+    int n_cols = 0;
+    for (int j = 0; j < VSR_MAX_VARS; ++j) a.col_of_var[j] = ((g.var_mask >> j) & 1u) ? n_cols++ : -1;
+    Geometry geo = choose_geometry(g.kmax == 0 ? 1 : ps.n, P, cap, opts->warps_per_run, g.kmax, g.K, g.max_insn,
+                                   g.max_imm, n_cols, elem, max_cluster, hook_seats > 0 ? hook_seats : kDefaultSeats);
+    if (g.kmax == 0) {  // runs without constants are only marked "not run": no points needed
+      geo.resident = 0;
+      geo.smem = vsr::fit_smem_bytes(geo.seats, g.kmax, g.K, geo.threads / 32, geo.cs, g.max_insn, g.max_imm, -1, 0, elem);
+    }
+    a.phase_cycles = h->phase_cycles;
+    a.resident = geo.resident;
+    a.tma_ok = tma_ok ? 1 : 0;
+    a.slice_stride = geo.stride;
+    a.seats = geo.seats;
+    a.kmax = g.kmax;
+    a.max_insn = g.max_insn;
+    a.max_imm = g.max_imm;
+    a.n_cols = n_cols;
+    a.queue = (int32_t*)h->d_queue.p + gi;
+    const int want_clusters = (n + geo.seats - 1) / geo.seats;
+    cudaError_t e = opts->eval_dtype == VSR_F64
+                        ? launch_fit<double>(g.K, a, geo.threads, geo.cs, geo.smem, want_clusters, gs)
+                        : launch_fit<float>(g.K, a, geo.threads, geo.cs, geo.smem, want_clusters, gs);
+    if (e != cudaSuccess)
+      return fail(h, VSR_ECUDA, "fit kernel launch failed (K=%d threads=%d cluster=%d seats=%d smem=%zu): %s", g.K,
+                  geo.threads, geo.cs, geo.seats, geo.smem, cudaGetErrorString(e));
+    h->launches += 1;
+    if (gi > 0) {
+      VSR_CUDA(h, cudaEventRecord(h->ev_join[gi - 1], gs));
+      VSR_CUDA(h, cudaStreamWaitEvent(st, h->ev_join[gi - 1], 0));
     }
   }
   if (h->profiling) VSR_CUDA(h, cudaEventRecord(ev_b, st));
@@ -851,7 +811,7 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
                       out_final_mse, nullptr, st);
   if (h->profiling) {
     VSR_CUDA(h, cudaEventRecord(ev_c, st));
-    h->spans.push_back({ev_a, ev_b, 0, (int)groups.size() * n_rounds});
+    h->spans.push_back({ev_a, ev_b, 0, (int)groups.size()});
     h->spans.push_back({ev_b, ev_c, 1, 2});
   }
   return rc;

@@ -58,7 +58,7 @@ struct FitOpts {
   int grad_mode;      // VsrGradMode
 };
 
-enum { VSR_NEED_EVAL = 1, VSR_DONE = 0, VSR_PAUSE = 2 /* kernel-level: round budget used up */ };
+enum { VSR_NEED_EVAL = 1, VSR_DONE = 0 };
 
 // lane context of fit_step / fit_init
 struct Lanes {
@@ -141,24 +141,6 @@ struct FitState {
 
 // number of doubles of workspace fit_init() carves for a run with k constants
 VSR_HDN inline int fit_workspace_doubles(int k) { return 11 * k + k * k; }
-
-// (re)points the vector members into a workspace; used by fit_init and when a paused run
-// is resumed from its saved image (the image keeps stale addresses)
-VSR_HDN inline void fit_rebase(FitState& S, int k, double* ws) {
-  S.k = k;
-  S.xe = ws;
-  S.rg = ws + k;
-  S.cx = ws + 2 * k;
-  S.cg = ws + 3 * k;
-  S.lastx = ws + 4 * k;
-  S.xk = ws + 5 * k;
-  S.gfk = ws + 6 * k;
-  S.pk = ws + 7 * k;
-  S.xt = ws + 8 * k;
-  S.gnew = ws + 9 * k;
-  S.Hy = ws + 10 * k;
-  S.H = ws + 11 * k;
-}
 
 VSR_HDN inline void fit_init(FitState& S, int k, double* ws, const double* x0) {
   S.k = k;

@@ -7,7 +7,7 @@
 namespace vsr {
 
 template <typename T, int K>
-cudaError_t launch_fit_T(const FitArgs& a, int threads, int cs, size_t smem, cudaStream_t st) {
+cudaError_t launch_fit_T(const FitArgs& a, int threads, int cs, size_t smem, int clusters, cudaStream_t st) {
   constexpr int P = points_per_thread(K);
   auto kern = fit_kernel<T, K, P>;
   if (threads > fit_max_threads<T, K>()) return cudaErrorInvalidConfiguration;
@@ -19,7 +19,7 @@ cudaError_t launch_fit_T(const FitArgs& a, int threads, int cs, size_t smem, cud
     if (e != cudaSuccess) return e;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)a.n_runs * cs);
+  cfg.gridDim = dim3((unsigned)cs);
   cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -30,6 +30,11 @@ cudaError_t launch_fit_T(const FitArgs& a, int threads, int cs, size_t smem, cud
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  int resident = 0;
+  e = cudaOccupancyMaxActiveClusters(&resident, kern, &cfg);
+  if (e != cudaSuccess) return e;
+  if (resident < 1) return cudaErrorLaunchOutOfResources;
+  cfg.gridDim = dim3((unsigned)(std::max(1, std::min(clusters, resident)) * cs));
   return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
@@ -42,7 +47,7 @@ cudaError_t launch_eval_T(const EvalArgs& a, int threads, size_t smem, cudaStrea
   return cudaGetLastError();
 }
 
-template cudaError_t launch_fit_T<VSR_INST_T, VSR_INST_K>(const FitArgs&, int, int, size_t, cudaStream_t);
+template cudaError_t launch_fit_T<VSR_INST_T, VSR_INST_K>(const FitArgs&, int, int, size_t, int, cudaStream_t);
 template cudaError_t launch_eval_T<VSR_INST_T, VSR_INST_K>(const EvalArgs&, int, size_t, cudaStream_t);
 
 }  // namespace vsr

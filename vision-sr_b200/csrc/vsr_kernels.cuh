@@ -43,10 +43,12 @@ struct Points {
   int64_t ldx;
 };
 
+constexpr int kMaxSeats = 8;  // runs a cluster can work on at a time
+
 struct FitArgs {
   ProgramTable pt;
   Points pts;
-  const int32_t* run_prog;  // [n_runs] (this launch's group)
+  const int32_t* run_prog;  // [n_runs] (this launch's group), in queue order
   const int32_t* run_slot;  // [n_runs]
   int32_t n_runs;
   int32_t kstride;
@@ -58,15 +60,13 @@ struct FitArgs {
   int32_t resident;      // 1: every CTA stages its slice of the points into shared memory
   int32_t tma_ok;        // 1: column starts and strides are 16-byte aligned (bulk copies)
   int32_t slice_stride;  // elements between columns of the staged slice
-  long long* phase_cycles;  // optional [n_slots][8]: SM cycles per phase of the pass loop (leader thread 0)
-  // budgeted rounds: a run that has not finished after `max_passes` sweeps of this launch saves
-  // its optimiser image and exits; the next launch resumes it (resume = 1).  Finished runs are
-  // flagged in run_done and their clusters exit at once.
-  unsigned char* state;     // [n_slots][state_stride] bytes: FitState image | timer | workspace
-  int32_t* run_done;        // [n_slots]
-  int32_t state_stride;
-  int32_t max_passes;       // <= 0: unlimited
-  int32_t resume;
+  int32_t seats;         // runs in flight per cluster (<= warps per CTA, <= kMaxSeats)
+  int32_t kmax, max_insn, max_imm;  // maxima over this launch's programs (size the seat areas)
+  int32_t n_cols;                   // columns of X this launch's programs read
+  int32_t col_of_var[VSR_MAX_VARS]; // slice column of variable j (-1: unused)
+  int32_t* queue;           // [1] index of the next run to hand out (zeroed by the host)
+  long long* phase_cycles;  // optional [n_slots][8]: cycles of the seat's optimiser lane 0:
+                            // [0] optimiser logic, [3] everything else while seated, [7] passes
   FitOpts O;
 };
 
@@ -278,86 +278,91 @@ __device__ __forceinline__ void sweep_slice(const vsr_insn_t* prog, const double
 }
 
 // ---- fit kernel ------------------------------------------------------------------------------------
-// One thread-block CLUSTER per (candidate, restart) run.  The points are split in
-// contiguous slices, one per CTA of the cluster.  When a slice fits, its used columns and
-// y are staged ONCE into the CTA's shared memory by TMA bulk copies and stay there for
-// every pass of the run (hundreds to thousands): the whole data set lives in the
-// cluster's distributed shared memory and HBM/L2 is read once per run.  CTA 0 (the
-// leader) owns the optimiser state; per pass the other CTAs read the trial constants from
-// the leader's shared memory and write their partial sums into it (DSMEM), with two
-// cluster barriers.  Reduction order is fixed (lanes, warps, CTA rank).
+// PERSISTENT thread-block clusters, each working on `seats` (candidate, restart) runs at a time.
 //
-// dynamic shared memory, in bytes (16-byte aligned sections):
-//   ws[fit_workspace_doubles(k)] | cred[cs*(K+1)] | red[nwarps*(K+1)] | cst[k+1] | imm | insn |
-//   slice: (n_slots + 1) * stride * sizeof(T)
-__host__ __device__ inline size_t fit_smem_bytes(int kmax, int K, int nwarps, int cs, int n_insn,
-                                                 int n_imm, int n_slots, int stride, int elem) {
-  size_t dbl = (size_t)fit_workspace_doubles(kmax) + (size_t)cs * (K + 1) + (size_t)nwarps * (K + 1) +
-               kmax + 1 + n_imm + n_insn + 2;
-  dbl = (dbl + 1) & ~(size_t)1;  // 16-byte boundary
-  return dbl * 8 + (size_t)(n_slots + 1) * stride * elem;
+// A pass of one run is: optimiser step (one warp, ~5-10 k cycles of dependent scalar work) ->
+// sweep of all points through the interpreter (all warps of all CTAs) -> reduction.  With one run
+// per cluster every warp but one idles through the optimiser step and both cluster barriers
+// (ncu: two thirds of all warp samples sat in barrier waits).  Here a cluster holds G runs in
+// "seats"; the G optimiser steps run CONCURRENTLY on warps 0..G-1 of the leader CTA, then all
+// warps sweep the G requests back to back, so the serial part is paid once per G sweeps.  A seat
+// whose run finishes takes the next run from the launch's queue (one atomic), so seats stay
+// full until the queue drains; the last long runs then have their cluster to themselves and
+// advance at single-run latency.
+//
+// The points are split in contiguous slices, one per CTA.  When a slice fits, the columns the
+// launch's programs read and y are staged ONCE per cluster into shared memory by TMA bulk
+// copies and stay there for every pass of every run the cluster handles.  Reduction order is
+// fixed (lanes, warps, CTA rank), so a run's result does not depend on its seat or cluster.
+//
+// dynamic shared memory (doubles):  per seat [ ws | cred[cs*(K+1)] | red[nw*(K+1)] | cst[kmax+1] |
+//   imm[max_imm] | insn[max_insn] ]  then the slice: (n_cols + 1) * stride * sizeof(T)
+__host__ __device__ inline size_t fit_seat_doubles(int kmax, int K, int nwarps, int cs, int max_insn,
+                                                   int max_imm) {
+  size_t d = (size_t)fit_workspace_doubles(kmax) + (size_t)cs * (K + 1) + (size_t)nwarps * (K + 1) +
+             kmax + 1 + max_imm + max_insn;
+  return (d + 1) & ~(size_t)1;  // 16-byte multiple
+}
+__host__ __device__ inline size_t fit_smem_bytes(int seats, int kmax, int K, int nwarps, int cs,
+                                                 int max_insn, int max_imm, int n_cols, int stride,
+                                                 int elem) {
+  return (size_t)seats * fit_seat_doubles(kmax, K, nwarps, cs, max_insn, max_imm) * 8 +
+         (n_cols >= 0 ? (size_t)(n_cols + 1) * stride * elem : 0);
 }
 
 // Widest CTA the fit kernel is compiled for.  320 threads at <= 96 registers lets TWO CTAs
-// (of different clusters, i.e. different runs) share an SM: while one run's cluster sits in
-// its optimiser step or a cluster barrier the other one sweeps.
+// (of different clusters) share an SM.
+#if !defined(VSR_FIT_THREADS)
+#define VSR_FIT_THREADS 320
+#define VSR_FIT_MINCTAS 2
+#endif
 template <typename T, int K>
 __host__ __device__ constexpr int fit_max_threads() {
-  return (sizeof(T) == 8 && K > 8) ? 256 : 320;
+  return (sizeof(T) == 8 && K > 8) ? 256 : VSR_FIT_THREADS;
 }
 template <typename T, int K>
 __host__ __device__ constexpr int fit_min_ctas() {
-  return (sizeof(T) == 8 && K > 8) ? 1 : 2;
+  return (sizeof(T) == 8 && K > 8) ? 1 : VSR_FIT_MINCTAS;
 }
 
 // The optimiser step, out of line: its register and stack needs stay out of the sweep's
-// allocation (the sweep is the hot loop; this runs on one warp between sweeps).
+// allocation (the sweep is the hot loop; this runs on one warp per seat between sweeps).
 static __device__ __noinline__ int fit_step_call(FitState& S, const FitOpts& O) { return fit_step(S, O); }
+
+struct SeatCtrl {
+  int prog;   // program of the seated run, -1: seat empty
+  int k;      // its number of constants
+  int fresh;  // 1: the run was seated in this pass (every CTA must load its program)
+  int pad;
+};
 
 template <typename T, int K, int P>
 __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>())) fit_kernel(const FitArgs a) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) double smem[];
-  FitState S;  // private per lane; only warp 0 of the leader CTA runs the optimiser
-  __shared__ double s_rf;
-  __shared__ int s_action;
-  __shared__ unsigned long long s_t0;
+  FitState S;  // private per lane; warp g of the leader CTA runs the optimiser of seat g
+  __shared__ SeatCtrl s_ctrl[kMaxSeats];
+  __shared__ double s_rf[kMaxSeats];
+  __shared__ unsigned long long s_t0[kMaxSeats];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_slot_of[VSR_MAX_VARS];
 
   const int cs = (int)cluster.num_blocks();
   const int crank = (int)cluster.block_rank();
-  const int run = blockIdx.x / cs;
-  const int prog = a.run_prog[run];
-  const int slot = a.run_slot[run];
-  const int k = a.pt.k[prog];
   const int nw = (blockDim.x + 31) >> 5;
   const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int G = a.seats;
 
-  double* ws = smem;
-  double* cred = ws + fit_workspace_doubles(k);
-  double* red = cred + cs * (K + 1);
-  T* cst = reinterpret_cast<T*>(red + nw * (K + 1));
-  double* s_imm = red + nw * (K + 1) + k + 1;
-  if (a.resume && a.run_done[slot]) return;  // finished in an earlier round; uniform over the cluster
-  int n_insn, n_imm;
-  const int m_imm = a.pt.imm_off[prog + 1] - a.pt.imm_off[prog];
-  vsr_insn_t* s_insn = reinterpret_cast<vsr_insn_t*>(s_imm + m_imm);
-  load_program(a.pt, prog, s_insn, s_imm, n_insn, n_imm);
-
-  int32_t* info = a.out_info + (int64_t)slot * 4;
-  if (k == 0) {  // nothing to optimise (reference bfgs.py:117-118); uniform over the cluster
-    if (crank == 0 && tid == 0) {
-      info[0] = VSR_FIT_NOT_RUN;
-      info[1] = 0;
-      info[2] = 0;
-      info[3] = 0;
-      a.out_loss[slot] = 0.0;
-      if (a.run_done) a.run_done[slot] = 1;
-    }
-    return;
-  }
+  const size_t seat_d = fit_seat_doubles(a.kmax, K, nw, cs, a.max_insn, a.max_imm);
+  const int wsd = fit_workspace_doubles(a.kmax);
+#define VSR_SEAT_WS(g) (smem + (size_t)(g)*seat_d)
+#define VSR_SEAT_CRED(g) (VSR_SEAT_WS(g) + wsd)
+#define VSR_SEAT_RED(g) (VSR_SEAT_CRED(g) + cs * (K + 1))
+#define VSR_SEAT_CST(g) (reinterpret_cast<T*>(VSR_SEAT_RED(g) + nw * (K + 1)))
+#define VSR_SEAT_IMM(g) (VSR_SEAT_RED(g) + nw * (K + 1) + a.kmax + 1)
+#define VSR_SEAT_INSN(g) (reinterpret_cast<vsr_insn_t*>(VSR_SEAT_IMM(g) + a.max_imm))
 
   // ---- this CTA's slice of the points ----
   const int64_t N = a.pts.n;
@@ -374,195 +379,225 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   T* ys = nullptr;
   const int stride = a.slice_stride;
   if (a.resident) {
-    size_t off = (size_t)((reinterpret_cast<char*>(s_insn + n_insn) - reinterpret_cast<char*>(smem)) + 15) &
-                 ~(size_t)15;
-    ys = reinterpret_cast<T*>(reinterpret_cast<char*>(smem) + off);
+    ys = reinterpret_cast<T*>(smem + (size_t)G * seat_d);
     xs = ys + stride;
-    __syncthreads();  // program is in shared memory
     constexpr int kAlign = 16 / (int)sizeof(T);
     const int full = cnt & ~(kAlign - 1);  // elements per column that move as 16-byte units
     const bool use_tma = a.tma_ok && full > 0;
-    if (tid == 0) {
-      // rewrite VAR operands to slice column slots, in first-use order
-      for (int j = 0; j < VSR_MAX_VARS; ++j) s_slot_of[j] = -1;
-      int ns = 0;
-      for (int i = 0; i < n_insn; ++i) {
-        const vsr_insn_t w = s_insn[i];
-        const unsigned op = VSR_OP(w);
-        if (op >= VSR_LOAD && op <= VSR_RPOW && op != VSR_PUSH && VSR_SRC(w) == VSR_SRC_VAR) {
-          const unsigned j = VSR_IDX(w);
-          if (s_slot_of[j] < 0) s_slot_of[j] = ns++;
-          s_insn[i] = (w & ~((vsr_insn_t)0xffff << 16)) | ((vsr_insn_t)s_slot_of[j] << 16);
-        }
-      }
-      if (use_tma) {
-        const uint32_t bytes = (uint32_t)full * (uint32_t)sizeof(T);
-        mbar_init(&s_bar, 1);
-        mbar_fence_init();
-        mbar_expect_tx(&s_bar, bytes * (uint32_t)(ns + 1));
-        tma_bulk_load(ys, y + n0, bytes, &s_bar);
-        for (int j = 0; j < VSR_MAX_VARS; ++j)
-          if (s_slot_of[j] >= 0)
-            tma_bulk_load(xs + (size_t)s_slot_of[j] * stride, X + (int64_t)j * a.pts.ldx + n0, bytes, &s_bar);
-      }
+    if (tid == 0 && use_tma) {
+      const uint32_t bytes = (uint32_t)full * (uint32_t)sizeof(T);
+      mbar_init(&s_bar, 1);
+      mbar_fence_init();
+      mbar_expect_tx(&s_bar, bytes * (uint32_t)(a.n_cols + 1));
+      tma_bulk_load(ys, y + n0, bytes, &s_bar);
+      for (int j = 0; j < VSR_MAX_VARS; ++j)
+        if (a.col_of_var[j] >= 0)
+          tma_bulk_load(xs + (size_t)a.col_of_var[j] * stride, X + (int64_t)j * a.pts.ldx + n0, bytes, &s_bar);
     }
-    __syncthreads();  // slot table, rewritten program and the armed barrier are visible
+    __syncthreads();  // the armed barrier is visible
     {
       // everything TMA does not move (all of it when the caller's memory is unaligned): coalesced loads
       const int first = use_tma ? full : 0;
       for (int i = first + tid; i < cnt; i += blockDim.x) ys[i] = y[n0 + i];
       for (int j = 0; j < VSR_MAX_VARS; ++j) {
-        const int sj = s_slot_of[j];
+        const int sj = a.col_of_var[j];
         if (sj < 0) continue;
         for (int i = first + tid; i < cnt; i += blockDim.x)
           xs[(size_t)sj * stride + i] = X[(int64_t)j * a.pts.ldx + n0 + i];
       }
     }
     if (use_tma) mbar_wait(&s_bar, 0);  // every thread observes the completed transaction
-    __syncthreads();
   }
-
-  // handler ids over the opcode bytes (after the slot rewrite, which reads raw opcodes)
-  __syncthreads();
-  for (int i = tid; i < n_insn; i += blockDim.x) s_insn[i] = predecode(s_insn[i]);
-  __syncthreads();
-
-  const bool is_logic = crank == 0 && tid < 32;  // warp 0 of the leader: the optimiser
-  unsigned char* image = a.state ? a.state + (int64_t)slot * a.state_stride : nullptr;
-  constexpr int kImgHead = (int)((sizeof(FitState) + 8 + 15) / 16 * 16);  // FitState | s_t0, 16-aligned
-  if (is_logic) {
-    if (a.resume) {
-      // every lane takes its own copy of the saved scalar state, the vectors go back to
-      // shared memory, and the pending evaluation request (S.xe) is served first
-      const FitState* saved = reinterpret_cast<const FitState*>(image);
-      S = *saved;
-      fit_rebase(S, k, ws);
-      const double* wsg = reinterpret_cast<const double*>(image + kImgHead);
-      for (int i = tid; i < fit_workspace_doubles(k); i += 32) ws[i] = wsg[i];
-      if (tid == 0) s_t0 = *reinterpret_cast<const unsigned long long*>(image + sizeof(FitState));
-      __syncwarp();
-    } else {
-      fit_init(S, k, ws, a.x0 + (int64_t)slot * a.kstride);
-      if (tid == 0) s_t0 = 0ull;
-    }
+  if (tid < kMaxSeats) {
+    s_ctrl[tid].prog = -1;
+    s_ctrl[tid].k = 0;
+    s_ctrl[tid].fresh = 0;
+    s_t0[tid] = 0ull;
   }
-  // leader state is initialised and every CTA of the cluster is running before any DSMEM access
-  cluster.sync();
+  __syncthreads();
 
-  const int* r_action = cluster.map_shared_rank(&s_action, 0);
-  const double* r_xe = cluster.map_shared_rank(ws, 0);  // FitState.xe is the first k doubles of ws
-  double* r_cred = cluster.map_shared_rank(cred, 0);
+  // ---- optimiser lanes: warp g of the leader CTA owns seat g ----
+  const bool is_logic = crank == 0 && warp < G;
+  const int seat = warp;
+  double* ws = VSR_SEAT_WS(is_logic ? seat : 0);
+  int my_prog = -1, my_slot = -1, my_k = 0;  // the run in this warp's seat (logic warps only)
+  bool drained = false;
+  const bool timing = a.phase_cycles != nullptr && is_logic && lane == 0;
+  long long t_logic = 0, t_seated = 0, n_pass = 0;
   const double inv_n = 1.0 / (double)N;
 
-  // optional phase timing (measurement aid): cycles of the leader's thread 0 in
-  // [0] optimiser logic  [1] first cluster barrier  [2] constant broadcast  [3] sweep
-  // [4] CTA reduction  [5] second cluster barrier  [6] finalisation  [7] passes
-  const bool timing = a.phase_cycles != nullptr && crank == 0 && tid == 0;
-  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  long long tprev = timing ? clock64() : 0;
-#define VSR_PHASE(i)                 \
-  if (timing) {                      \
-    const long long tn = clock64();  \
-    ph[i] += tn - tprev;             \
-    tprev = tn;                      \
-  }
+  // every CTA of the cluster is running (and has its seat table initialised) before any DSMEM access
+  cluster.sync();
+  const SeatCtrl* r_ctrl = cluster.map_shared_rank(s_ctrl, 0);
+  double* r_smem = cluster.map_shared_rank(smem, 0);
 
-  int passes = 0;
-  bool pending = a.resume != 0;  // a resumed run re-enters at its saved evaluation request
   for (;;) {
+    // ---- phase A: optimiser steps, one warp per seat, concurrently ----
     if (is_logic) {
-      int act = VSR_NEED_EVAL;
-      if (!pending) act = fit_step_call(S, a.O);
-      if (act == VSR_NEED_EVAL && a.max_passes > 0 && passes >= a.max_passes) {
-        // budget of this round used up: save the image, stop here (the request stays pending)
-        act = VSR_PAUSE;
-        __syncwarp();
-        if (tid == 0) {
-          *reinterpret_cast<FitState*>(image) = S;
-          *reinterpret_cast<unsigned long long*>(image + sizeof(FitState)) = s_t0;
+      long long ta = timing ? clock64() : 0;
+      int fresh = 0;
+      for (;;) {
+        if (my_prog < 0) {  // empty seat: take the next run of the launch
+          int r = -1;
+          if (!drained) {
+            if (lane == 0) r = atomicAdd(a.queue, 1);
+            r = __shfl_sync(0xffffffffu, r, 0);
+            if (r >= a.n_runs) {
+              drained = true;
+              r = -1;
+            }
+          }
+          if (r < 0) break;
+          const int prog = a.run_prog[r];
+          const int slot = a.run_slot[r];
+          const int k = a.pt.k[prog];
+          if (k == 0) {  // nothing to optimise (reference bfgs.py:117-118)
+            if (lane == 0) {
+              int32_t* info = a.out_info + (int64_t)slot * 4;
+              info[0] = VSR_FIT_NOT_RUN;
+              info[1] = 0;
+              info[2] = 0;
+              info[3] = 0;
+              a.out_loss[slot] = 0.0;
+            }
+            continue;
+          }
+          my_prog = prog;
+          my_slot = slot;
+          my_k = k;
+          fresh = 1;
+          fit_init(S, k, ws, a.x0 + (int64_t)slot * a.kstride);
+          if (lane == 0) s_t0[seat] = 0ull;
+          if (timing) t_seated = clock64(), t_logic = 0, n_pass = 0;
         }
-        double* wsg = reinterpret_cast<double*>(image + kImgHead);
-        for (int i = tid; i < fit_workspace_doubles(k); i += 32) wsg[i] = ws[i];
+        const int act = fit_step_call(S, a.O);
+        if (act == VSR_NEED_EVAL) break;
+        // finished: results out, seat free, try to seat another run in this same pass
+        __syncwarp();
+        if (lane == 0) {
+          double* oc = a.out_consts + (int64_t)my_slot * a.kstride;
+          double* ol = a.out_lastx + (int64_t)my_slot * a.kstride;
+          for (int i = 0; i < my_k; ++i) {
+            oc[i] = S.xk[i];
+            ol[i] = S.lastx[i];
+          }
+          a.out_loss[my_slot] = S.old_fval;
+          int32_t* info = a.out_info + (int64_t)my_slot * 4;
+          info[0] = S.status;
+          info[1] = S.it;
+          info[2] = S.nfev;
+          info[3] = 0;
+          if (timing) {
+            const long long now = clock64();
+            t_logic += now - ta;
+            ta = now;
+            long long* ph = a.phase_cycles + (int64_t)my_slot * 8;
+            ph[0] += t_logic;
+            ph[3] += (now - t_seated) - t_logic;
+            ph[7] += n_pass;
+          }
+        }
+        __syncwarp();
+        my_prog = -1;
+        fresh = 0;
       }
-      if (tid == 0) s_action = act;
+      if (lane == 0) {
+        s_ctrl[seat].prog = my_prog;
+        s_ctrl[seat].k = my_k;
+        s_ctrl[seat].fresh = fresh;
+      }
+      if (timing && my_prog >= 0) t_logic += clock64() - ta;
     }
-    pending = false;
-    ++passes;
-    VSR_PHASE(0)
-    cluster.sync();
-    VSR_PHASE(1)
-    if (*r_action != VSR_NEED_EVAL) break;
-    // trial constants from the leader, in the arithmetic type of the sweep
-    for (int i = tid; i < k; i += blockDim.x) cst[i] = (T)r_xe[i];
+    cluster.sync();  // requests (seat table, trial constants) are visible to every CTA
+
+    // ---- phase B: every CTA sweeps its slice for every occupied seat ----
+    int active = 0;
+    for (int g = 0; g < G; ++g) {
+      const SeatCtrl c = r_ctrl[g];
+      if (c.prog < 0) continue;
+      active |= 1 << g;
+      if (c.fresh) {
+        // the run was seated in this pass: its program into this CTA's seat area, VAR operands
+        // rewritten to slice columns, handler ids over the opcode bytes
+        const int i0 = a.pt.insn_off[c.prog], ni = a.pt.insn_off[c.prog + 1] - i0;
+        const int m0 = a.pt.imm_off[c.prog], nm = a.pt.imm_off[c.prog + 1] - m0;
+        vsr_insn_t* s_insn = VSR_SEAT_INSN(g);
+        double* s_imm = VSR_SEAT_IMM(g);
+        for (int i = tid; i < ni; i += blockDim.x) {
+          vsr_insn_t w = a.pt.insns[i0 + i];
+          const unsigned op = VSR_OP(w);
+          if (a.resident && op >= VSR_LOAD && op <= VSR_RPOW && op != VSR_PUSH && VSR_SRC(w) == VSR_SRC_VAR)
+            w = (w & ~((vsr_insn_t)0xffff << 16)) | ((vsr_insn_t)a.col_of_var[VSR_IDX(w)] << 16);
+          s_insn[i] = predecode(w);
+        }
+        for (int i = tid; i < nm; i += blockDim.x) s_imm[i] = a.pt.imms[m0 + i];
+      }
+      // trial constants from the leader's workspace (FitState.xe is its first k doubles), in
+      // the arithmetic type of the sweep
+      const double* r_xe = r_smem + (size_t)g * seat_d;
+      T* cst = VSR_SEAT_CST(g);
+      for (int i = tid; i < c.k; i += blockDim.x) cst[i] = (T)r_xe[i];
+    }
+    if (!active) break;  // no seated run and the queue is drained: uniform over the cluster
     __syncthreads();
-    VSR_PHASE(2)
-    double s, g[K > 0 ? K : 1];
-    if (a.resident)
-      sweep_slice<T, K, P>(s_insn, s_imm, cst, xs, ys, stride, cnt, s, g);
-    else
-      sweep_points<T, K, P>(s_insn, s_imm, cst, X, y, a.pts.ldx, n0, n1, s, g);
-    VSR_PHASE(3)
-    block_sum<K>(s, g, red);
-    if (tid == 0) {
-      r_cred[crank * (K + 1)] = s;
+    for (int g = 0; g < G; ++g) {
+      if (!((active >> g) & 1)) continue;
+      double s, gsum[K > 0 ? K : 1];
+      if (a.resident)
+        sweep_slice<T, K, P>(VSR_SEAT_INSN(g), VSR_SEAT_IMM(g), VSR_SEAT_CST(g), xs, ys, stride, cnt, s, gsum);
+      else
+        sweep_points<T, K, P>(VSR_SEAT_INSN(g), VSR_SEAT_IMM(g), VSR_SEAT_CST(g), X, y, a.pts.ldx, n0, n1, s, gsum);
+      block_sum<K>(s, gsum, VSR_SEAT_RED(g));
+      if (tid == 0) {
+        double* r_cred = r_smem + (size_t)g * seat_d + wsd;
+        r_cred[crank * (K + 1)] = s;
 #pragma unroll
-      for (int t = 0; t < K; ++t) r_cred[crank * (K + 1) + 1 + t] = g[t];
+        for (int t = 0; t < K; ++t) r_cred[crank * (K + 1) + 1 + t] = gsum[t];
+      }
     }
-    VSR_PHASE(4)
-    cluster.sync();
-    VSR_PHASE(5)
-    if (is_logic) {
-      // component `tid` of (sum r^2, sum r df/dc_t) over the CTAs of the cluster in rank
+    cluster.sync();  // every CTA's partial sums are in the leader's shared memory
+
+    // ---- phase C: responses, to every lane's private optimiser state ----
+    if (is_logic && my_prog >= 0) {
+      const long long tc = timing ? clock64() : 0;
+      // component `lane` of (sum r^2, sum r df/dc_t) over the CTAs of the cluster in rank
       // order; lane 0 applies the penalty rule, lanes 1..k scale the gradient
+      const double* cred = VSR_SEAT_CRED(seat);
       double tot = 0.0;
-      if (tid <= K)
-        for (int r = 0; r < cs; ++r) tot += cred[r * (K + 1) + tid];
+      if (lane <= K)
+        for (int r = 0; r < cs; ++r) tot += cred[r * (K + 1) + lane];
       const double f = a.O.loss_scale * (__shfl_sync(0xffffffffu, tot, 0) * inv_n);
       bool bad = !isfinite(f);
       if (a.O.stop_time < 1e8) {  // TimedFun (bfgs.py:29-33): the clock starts at the first call
         int late = 0;
-        if (tid == 0) {
+        if (lane == 0) {
           const unsigned long long now = global_ns();
-          if (s_t0 == 0ull)
-            s_t0 = now;
-          else if ((double)(now - s_t0) * 1e-9 >= a.O.stop_time)
+          if (s_t0[seat] == 0ull)
+            s_t0[seat] = now;
+          else if ((double)(now - s_t0[seat]) * 1e-9 >= a.O.stop_time)
             late = 1;
         }
         if (__shfl_sync(0xffffffffu, late, 0)) bad = true;
       }
-      if (tid == 0) s_rf = bad ? a.O.penalty : f;
-      if (tid >= 1 && tid <= K && tid - 1 < k) {
+      if (lane == 0) s_rf[seat] = bad ? a.O.penalty : f;
+      if (lane >= 1 && lane <= K && lane - 1 < my_k) {
         const double gv = a.O.loss_scale * (2.0 * tot * inv_n);
-        S.rg[tid - 1] = (bad || !isfinite(gv)) ? 0.0 : gv;
+        S.rg[lane - 1] = (bad || !isfinite(gv)) ? 0.0 : gv;
       }
-      if (tid == 0) ph[7] += 1;
-    }
-    if (is_logic) {  // the response, to every lane's private optimiser state
       __syncwarp();
-      S.rf = s_rf;
+      S.rf = s_rf[seat];
+      if (timing) {
+        t_logic += clock64() - tc;
+        n_pass += 1;
+      }
     }
-    VSR_PHASE(6)
-    // the leader's warp 0 goes straight back into fit_step; everyone else waits at the
-    // cluster barrier above
   }
-#undef VSR_PHASE
-  if (timing)
-    for (int i = 0; i < 8; ++i) a.phase_cycles[(int64_t)slot * 8 + i] += ph[i];
-
-  if (crank == 0 && tid == 0 && s_action == VSR_DONE) {
-    if (a.run_done) a.run_done[slot] = 1;
-    double* oc = a.out_consts + (int64_t)slot * a.kstride;
-    double* ol = a.out_lastx + (int64_t)slot * a.kstride;
-    for (int i = 0; i < k; ++i) {
-      oc[i] = S.xk[i];
-      ol[i] = S.lastx[i];
-    }
-    a.out_loss[slot] = S.old_fval;
-    info[0] = S.status;
-    info[1] = S.it;
-    info[2] = S.nfev;
-    info[3] = 0;
-  }
+#undef VSR_SEAT_WS
+#undef VSR_SEAT_CRED
+#undef VSR_SEAT_RED
+#undef VSR_SEAT_CST
+#undef VSR_SEAT_IMM
+#undef VSR_SEAT_INSN
   // no CTA may exit while another can still read its shared memory
   cluster.sync();
 }

@@ -12,7 +12,9 @@ namespace vsr {
 constexpr int points_per_thread(int K) { return K <= 8 ? 2 : 1; }
 
 template <typename T, int K>
-cudaError_t launch_fit_T(const FitArgs& a, int threads, int cs, size_t smem, cudaStream_t st);
+// `clusters`: how many clusters the launch could use (runs / seats); clamped to what the device
+// can keep resident, since the clusters are persistent
+cudaError_t launch_fit_T(const FitArgs& a, int threads, int cs, size_t smem, int clusters, cudaStream_t st);
 
 template <typename T, int K>
 cudaError_t launch_eval_T(const EvalArgs& a, int threads, size_t smem, cudaStream_t st);
