@@ -25,15 +25,17 @@ for sc in scheds:
     else: os.environ.pop("VSR_GEOMETRY", None)
     ms = []
     losses = []
+    nfev = 0
     for rep in range(2):
         ms = []
         for eng, x0d, rp, rs in setups:
             s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
             s.record(); res = eng.fit(rp, rs, x0d); e.record(); torch.cuda.synchronize()
             ms.append(s.elapsed_time(e))
-            if rep == 1: losses.append(res.loss.cpu().numpy().copy())
+            if rep == 1:
+                losses.append(res.loss.cpu().numpy().copy()); nfev += int(res.info[:, 2].sum())
     L = np.concatenate(losses)
     same = "" if ref is None else f" close_to_first={np.mean(np.isclose(L, ref, rtol=1e-6, atol=1e-9, equal_nan=True)):.4f}"
     if ref is None: ref = L
-    print(f"sched={sc or 'builtin':28s} total={sum(ms):8.1f} ms  mean={np.mean(ms):6.1f}  max={max(ms):6.1f}{same}", flush=True)
+    print(f"sched={sc or 'builtin':28s} total={sum(ms):8.1f} ms  mean={np.mean(ms):6.1f}  max={max(ms):6.1f}  passes={nfev}  us/kpass={1e6*sum(ms)/max(1,nfev):7.1f}{same}", flush=True)
     if len(scheds) <= 2: print("   per beam:", " ".join(f"{b.name}:{m:.0f}" for b, m in zip(beams, ms)))

@@ -14,7 +14,7 @@
 
 namespace {
 
-constexpr int kWidths[] = {0, 1, 2, 3, 4, 6, 8, 12, 16};
+constexpr int kWidths[] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 12, 16};
 constexpr int kNumWidths = sizeof(kWidths) / sizeof(kWidths[0]);
 
 int pick_width(int k) {
@@ -176,7 +176,7 @@ template <typename T>
 cudaError_t launch_fit(int K, const vsr::FitArgs& a, int threads, int cs, size_t smem, int clusters, cudaStream_t st) {
   switch (K) {
 #define C(KK) case KK: return vsr::launch_fit_T<T, KK>(a, threads, cs, smem, clusters, st);
-    C(0) C(1) C(2) C(3) C(4) C(6) C(8) C(12) C(16)
+    C(0) C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(12) C(16)
 #undef C
   }
   return cudaErrorInvalidValue;
@@ -186,7 +186,7 @@ template <typename T>
 int fit_threads_cap(int K) {
   switch (K) {
 #define C(KK) case KK: return vsr::fit_max_threads<T, KK>();
-    C(0) C(1) C(2) C(3) C(4) C(6) C(8) C(12) C(16)
+    C(0) C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(12) C(16)
 #undef C
   }
   return 256;
@@ -196,7 +196,7 @@ template <typename T>
 cudaError_t launch_eval(int K, const vsr::EvalArgs& a, int threads, size_t smem, cudaStream_t st) {
   switch (K) {
 #define C(KK) case KK: return vsr::launch_eval_T<T, KK>(a, threads, smem, st);
-    C(0) C(1) C(2) C(3) C(4) C(6) C(8) C(12) C(16)
+    C(0) C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(12) C(16)
 #undef C
   }
   return cudaErrorInvalidValue;
@@ -220,7 +220,7 @@ struct Geometry {
 
 constexpr int kMaxCluster = 16;             // 16 needs the non-portable cluster size opt-in
 constexpr int kDefaultSeats = 4;            // runs in flight per cluster
-constexpr size_t kSmemBudget = 100 * 1024;  // per CTA: two CTAs per SM keep their slices resident
+constexpr size_t kSmemBudget = (VSR_FIT_MINCTAS == 1 ? 200 : 100) * 1024;  // per CTA, so that all co-resident CTAs keep their slices
 
 Geometry choose_geometry(int64_t N, int P, int cap_threads, int forced_warps, int kmax, int K, int max_insn,
                          int max_imm, int n_cols, int elem, int max_cluster, int seats) {

@@ -242,14 +242,21 @@ VSR_HD void unary_apply(Dual<T, K>& x, unsigned am, int n) {
 // single jump table: (opcode, operand source) pairs for LOAD and the binary ops, the opcode
 // alone for everything else.  Programs are "predecoded" (handler id written over the opcode
 // byte) when they are copied into shared memory.
-// ids are DENSE (0..54, no holes) so that the switch compiles to one indexed branch:
-//   0 END, 1 PUSH, 2..37 (LOAD, ADD..RPOW) x 4 sources, 38..54 the unary ops
+// ids are DENSE (0..63, no holes) so that the switch compiles to one indexed branch:
+//   0 END, 1 PUSH, 2..37 (LOAD, ADD..RPOW) x 4 sources, 38..54 the unary ops,
+//   55..118 LOAD / ADD / SUB / MUL with a FRESH fitted constant c_j as operand, one handler per
+//   (op, j): the tangent of c_j is structurally dead in acc (every skeleton the compiler emits
+//   names each constant once), so the one-hot operand tangent is WRITTEN into register slot j,
+//   known at compile time, instead of being added through K selects (tangent registers cannot
+//   be indexed at run time)
 #define VSR_H_BINOP(op) ((op) == VSR_LOAD ? 0 : (op)-VSR_ADD + 1)          /* 0..8 */
 #define VSR_H_BIN(op, src) (2 + ((VSR_H_BINOP(op)) << 2) + (src))          /* 2..37 */
 #define VSR_H_UN(op) (38 + (op)-VSR_NEG)                                   /* 38..54 */
+#define VSR_H_CFOP(op) ((op) == VSR_LOAD ? 0 : (op) == VSR_ADD ? 1 : (op) == VSR_SUB ? 2 : 3)
+#define VSR_H_CF(op, j) (55 + VSR_H_CFOP(op) * VSR_MAX_DUAL + (j))          /* 55..118 */
 #define VSR_H_END 0
 #define VSR_H_PUSH 1
-#define VSR_H_COUNT 55
+#define VSR_H_COUNT 119
 #define VSR_HANDLER(w) ((unsigned)((w)&0xff))
 
 VSR_HD vsr_insn_t predecode(vsr_insn_t w) {
@@ -259,6 +266,10 @@ VSR_HD vsr_insn_t predecode(vsr_insn_t w) {
     h = VSR_H_END;
   else if (op == VSR_PUSH)
     h = VSR_H_PUSH;
+  else if ((op == VSR_LOAD || op == VSR_ADD || op == VSR_SUB || op == VSR_MUL) &&
+           (VSR_SRC(w) & 3u) == VSR_SRC_CONST && VSR_IDX(w) < VSR_MAX_DUAL &&
+           (op == VSR_LOAD || !((VSR_AMASK(w) >> VSR_IDX(w)) & 1u)))
+    h = VSR_H_CF(op, VSR_IDX(w));
   else if (op <= VSR_RPOW)
     h = VSR_H_BIN(op, VSR_SRC(w) & 3u);
   else
@@ -413,6 +424,45 @@ VSR_HD void binary_apply(Dual<T, K> (&acc)[P], Stack<T, K, P>& stk, int& sp, uns
   }
 }
 
+// LOAD / ADD / SUB / MUL whose operand is the FRESH fitted constant c_J (its tangent is
+// structurally dead in acc).  Same formulas as binary_apply<OP, VSR_SRC_CONST> with
+// x.d[J] == 0; J is a compile-time register slot.
+template <int OP, int J, typename T, int K, int P>
+VSR_HD void const_fresh_apply(Dual<T, K> (&acc)[P], const T* __restrict__ cst) {
+  constexpr int JJ = (K > 0 && J < K) ? J : 0;
+  const T c = cst[J];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    Dual<T, K>& x = acc[p];
+    const T a = x.v;
+    switch (OP) {
+      case VSR_LOAD:
+        x.v = c;
+#pragma unroll
+        for (int i = 0; i < K; ++i) x.d[i] = T(0);
+        if (K > 0) x.d[JJ] = T(1);
+        break;
+      case VSR_ADD:
+        x.v = a + c;
+        if (K > 0) x.d[JJ] = T(1);
+        break;
+      case VSR_SUB:
+        x.v = a - c;
+        if (K > 0) x.d[JJ] = T(-1);
+        break;
+      case VSR_MUL:
+        x.v = a * c;
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+          if (i != JJ) x.d[i] *= c;
+        if (K > 0) x.d[JJ] = a;
+        break;
+      default:
+        break;
+    }
+  }
+}
+
 // Where the points come from: col(j, p) returns x_{j+1} of the p-th point of this call.
 // (a functor so the kernels can read global or shared memory and the host simulator a
 // plain array.)  `prog` must be predecoded.
@@ -468,6 +518,21 @@ VSR_HD void eval_points(const vsr_insn_t* __restrict__ prog, const double* __res
         VSR_BCASE(VSR_POW)
         VSR_BCASE(VSR_RPOW)
 #undef VSR_BCASE
+#define VSR_CFCASE1(OPC, J)                                              \
+  case VSR_H_CF(OPC, J):                                                 \
+    if (J < K || K == 0) const_fresh_apply<OPC, J, T, K, P>(acc, cst);   \
+    break;
+#define VSR_CFCASE(OPC)                                                                          \
+  VSR_CFCASE1(OPC, 0) VSR_CFCASE1(OPC, 1) VSR_CFCASE1(OPC, 2) VSR_CFCASE1(OPC, 3)                \
+  VSR_CFCASE1(OPC, 4) VSR_CFCASE1(OPC, 5) VSR_CFCASE1(OPC, 6) VSR_CFCASE1(OPC, 7)                \
+  VSR_CFCASE1(OPC, 8) VSR_CFCASE1(OPC, 9) VSR_CFCASE1(OPC, 10) VSR_CFCASE1(OPC, 11)              \
+  VSR_CFCASE1(OPC, 12) VSR_CFCASE1(OPC, 13) VSR_CFCASE1(OPC, 14) VSR_CFCASE1(OPC, 15)
+        VSR_CFCASE(VSR_LOAD)
+        VSR_CFCASE(VSR_ADD)
+        VSR_CFCASE(VSR_SUB)
+        VSR_CFCASE(VSR_MUL)
+#undef VSR_CFCASE
+#undef VSR_CFCASE1
 #define VSR_UCASE(OPC)                                                  \
   case VSR_H_UN(OPC):                                                   \
     _Pragma("unroll") for (int p = 0; p < P; ++p)                       \

@@ -295,12 +295,18 @@ __device__ __forceinline__ void sweep_slice(const vsr_insn_t* prog, const double
 // copies and stay there for every pass of every run the cluster handles.  Reduction order is
 // fixed (lanes, warps, CTA rank), so a run's result does not depend on its seat or cluster.
 //
-// dynamic shared memory (doubles):  per seat [ ws | cred[cs*(K+1)] | red[nw*(K+1)] | cst[kmax+1] |
+// dynamic shared memory (doubles):  per seat [ FitState | ws | cred[cs*(K+1)] | red[nw*(K+1)] | cst[kmax+1] |
 //   imm[max_imm] | insn[max_insn] ]  then the slice: (n_cols + 1) * stride * sizeof(T)
+// The optimiser state of a seat lives in SHARED memory, one copy per seat that all 32 lanes of
+// the seat's warp read (broadcast) and write (same value, uniform control flow).  As a per-lane
+// local variable it was evicted from L1 by every sweep's spill and operand-stack traffic, and
+// each pass re-read it from L2: 18-21 k cycles per optimiser step on an otherwise idle SM.
+constexpr int kFitStateDoubles = (int)((sizeof(FitState) + 15) / 16 * 2);
+
 __host__ __device__ inline size_t fit_seat_doubles(int kmax, int K, int nwarps, int cs, int max_insn,
                                                    int max_imm) {
-  size_t d = (size_t)fit_workspace_doubles(kmax) + (size_t)cs * (K + 1) + (size_t)nwarps * (K + 1) +
-             kmax + 1 + max_imm + max_insn;
+  size_t d = kFitStateDoubles + (size_t)fit_workspace_doubles(kmax) + (size_t)cs * (K + 1) +
+             (size_t)nwarps * (K + 1) + kmax + 1 + max_imm + max_insn;
   return (d + 1) & ~(size_t)1;  // 16-byte multiple
 }
 __host__ __device__ inline size_t fit_smem_bytes(int seats, int kmax, int K, int nwarps, int cs,
@@ -310,11 +316,14 @@ __host__ __device__ inline size_t fit_smem_bytes(int seats, int kmax, int K, int
          (n_cols >= 0 ? (size_t)(n_cols + 1) * stride * elem : 0);
 }
 
-// Widest CTA the fit kernel is compiled for.  320 threads at <= 96 registers lets TWO CTAs
-// (of different clusters) share an SM.
+// Widest CTA the fit kernel is compiled for: ONE CTA of 640 threads (20 warps at <= 96
+// registers) per SM, so a cluster owns its SMs.  Measured on the BASELINE config-2 beams
+// (tools/exp_schedules.py, us per 1000 sweeps): 8 CTAs x 640 threads 1034, 16 x 320 with two CTAs
+// per SM 1106, 16 x 160 with four 1070: optimiser steps run uncontended and a sweep of
+// N = 10 000 is one tile iteration.
 #if !defined(VSR_FIT_THREADS)
-#define VSR_FIT_THREADS 320
-#define VSR_FIT_MINCTAS 2
+#define VSR_FIT_THREADS 640
+#define VSR_FIT_MINCTAS 1
 #endif
 template <typename T, int K>
 __host__ __device__ constexpr int fit_max_threads() {
@@ -341,7 +350,6 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) double smem[];
-  FitState S;  // private per lane; warp g of the leader CTA runs the optimiser of seat g
   __shared__ SeatCtrl s_ctrl[kMaxSeats];
   __shared__ double s_rf[kMaxSeats];
   __shared__ unsigned long long s_t0[kMaxSeats];
@@ -357,7 +365,8 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
 
   const size_t seat_d = fit_seat_doubles(a.kmax, K, nw, cs, a.max_insn, a.max_imm);
   const int wsd = fit_workspace_doubles(a.kmax);
-#define VSR_SEAT_WS(g) (smem + (size_t)(g)*seat_d)
+#define VSR_SEAT_STATE(g) (smem + (size_t)(g)*seat_d)
+#define VSR_SEAT_WS(g) (VSR_SEAT_STATE(g) + kFitStateDoubles)
 #define VSR_SEAT_CRED(g) (VSR_SEAT_WS(g) + wsd)
 #define VSR_SEAT_RED(g) (VSR_SEAT_CRED(g) + cs * (K + 1))
 #define VSR_SEAT_CST(g) (reinterpret_cast<T*>(VSR_SEAT_RED(g) + nw * (K + 1)))
@@ -420,6 +429,8 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   const bool is_logic = crank == 0 && warp < G;
   const int seat = warp;
   double* ws = VSR_SEAT_WS(is_logic ? seat : 0);
+  // warp g of the leader CTA runs the optimiser of seat g on the seat's shared state
+  FitState& S = *reinterpret_cast<FitState*>(VSR_SEAT_STATE(is_logic ? seat : 0));
   int my_prog = -1, my_slot = -1, my_k = 0;  // the run in this warp's seat (logic warps only)
   bool drained = false;
   const bool timing = a.phase_cycles != nullptr && is_logic && lane == 0;
@@ -534,7 +545,7 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
       }
       // trial constants from the leader's workspace (FitState.xe is its first k doubles), in
       // the arithmetic type of the sweep
-      const double* r_xe = r_smem + (size_t)g * seat_d;
+      const double* r_xe = r_smem + (size_t)g * seat_d + kFitStateDoubles;
       T* cst = VSR_SEAT_CST(g);
       for (int i = tid; i < c.k; i += blockDim.x) cst[i] = (T)r_xe[i];
     }
@@ -549,7 +560,7 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
         sweep_points<T, K, P>(VSR_SEAT_INSN(g), VSR_SEAT_IMM(g), VSR_SEAT_CST(g), X, y, a.pts.ldx, n0, n1, s, gsum);
       block_sum<K>(s, gsum, VSR_SEAT_RED(g));
       if (tid == 0) {
-        double* r_cred = r_smem + (size_t)g * seat_d + wsd;
+        double* r_cred = r_smem + (size_t)g * seat_d + kFitStateDoubles + wsd;
         r_cred[crank * (K + 1)] = s;
 #pragma unroll
         for (int t = 0; t < K; ++t) r_cred[crank * (K + 1) + 1 + t] = gsum[t];
@@ -592,6 +603,7 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
       }
     }
   }
+#undef VSR_SEAT_STATE
 #undef VSR_SEAT_WS
 #undef VSR_SEAT_CRED
 #undef VSR_SEAT_RED

@@ -326,6 +326,24 @@ class _Lowering:
         return m
 
 
+def _peephole(code):
+    """NEG followed by ADD <operand>  ->  RSUB <operand>  (operand - acc).
+
+    Bit-exact: IEEE negation is exact and b + (-a) == b - a, for the value and for every
+    tangent.  sympy's canonical form writes x - y as Add(x, Mul(-1, y)), so this removes one
+    dispatch from every difference."""
+    out = []
+    for w in code:
+        op, src, idx, am, bm = isa.decode(w)
+        if out and op == OP["VSR_ADD"]:
+            pop, psrc, pidx, pam, pbm = isa.decode(out[-1])
+            if pop == OP["VSR_NEG"]:
+                out[-1] = isa.encode(OP["VSR_RSUB"], src, idx, am, bm)
+                continue
+        out.append(w)
+    return out
+
+
 def compile_sympy(expr, k, variables):
     """Lower a sympy expression in the symbols ``variables`` and ``c0..c{k-1}``."""
     if k > isa.MAX_CONSTS:
@@ -336,6 +354,7 @@ def compile_sympy(expr, k, variables):
     low = _Lowering(k, list(variables))
     low.gen(expr)
     low.emit("VSR_END")
+    low.code = _peephole(low.code)
     return Program(
         insns=np.asarray(low.code, dtype=np.uint64),
         imms=np.asarray(low.imms if low.imms else [0.0], dtype=np.float64),

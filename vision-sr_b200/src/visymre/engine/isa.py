@@ -52,7 +52,7 @@ MAX_INSNS = _DEFINES["VSR_MAX_INSNS"]
 MAX_IMMS = _DEFINES["VSR_MAX_IMMS"]
 
 # tangent widths the kernels are instantiated for (must match vsr_kernels.cu)
-DUAL_WIDTHS = (0, 1, 2, 3, 4, 6, 8, 12, 16)
+DUAL_WIDTHS = (0, 1, 2, 3, 4, 5, 6, 7, 8, 12, 16)
 
 
 def pick_dual_width(k):

@@ -11,7 +11,8 @@ import subprocess
 
 from . import isa
 
-LIB_PATH = os.path.join(isa.CSRC_DIR, "libvsr.so")
+# VSR_LIB: A/B measurement hook (another build of the same ABI)
+LIB_PATH = os.environ.get("VSR_LIB") or os.path.join(isa.CSRC_DIR, "libvsr.so")
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 c_f64p = ctypes.POINTER(ctypes.c_double)
