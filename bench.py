@@ -373,6 +373,12 @@ def main():
         derived = 148 * (128 if args.precision == "fp32" else 64) * 2 * sm_max * 1e6 / 1e12
         fp_peak = fp.get(key, derived)
         fp_src = "measured (profiles/fp_peaks.json)" if key in fp else f"derived: 148 SMs x lanes x 2 x {sm_max:.0f} MHz"
+        cap = None
+        try:   # DRAM bytes of one launch of the dominant kernel, from the committed ncu capture
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_capture.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        traffic = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) if cap else None
         fit_s = fit_ms_all / 1e3 / world      # per-rank average kernel time
         n_launch = max(1.0, fit_n_all)
         achieved_tf = flops_all / world / max(fit_s, 1e-9) / 1e12
@@ -398,7 +404,9 @@ def main():
                 "achieved": achieved_tf, "peak": fp_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp_peak,
                 "peak_source": fp_src,
                 "launch_ms": fit_ms_all / n_launch, "share_of_step": fit_ms_all / world / (total_ms_max or 1),
-                "traffic": None,
+                "traffic": traffic, "traffic_source": (cap or {}).get("source"),
+                "ncu": {k: cap[k] for k in ("kernel", "issue_active_pct", "pipe_fp64_pct", "pipe_alu_pct",
+                                            "pipe_lsu_pct", "duration_ms") if k in cap} if cap else None,
                 "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                         "peak_source": hbm_src},
                 "note": "algorithmic flops per SURVEY 8d (1 per arithmetic node, transcendental = 1); the kernel "
