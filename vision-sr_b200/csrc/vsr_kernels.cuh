@@ -66,7 +66,8 @@ struct FitArgs {
   int32_t col_of_var[VSR_MAX_VARS]; // slice column of variable j (-1: unused)
   int32_t* queue;           // [1] index of the next run to hand out (zeroed by the host)
   long long* phase_cycles;  // optional [n_slots][8]: cycles of the seat's optimiser lane 0:
-                            // [0] optimiser logic, [3] everything else while seated, [7] passes
+                            // [0] optimiser logic, [3] everything else while seated, [7] passes; runs of seat 0 also
+                            // carry the cluster's [1] barrier 1 [2] fetch [4] sweeps [5] barrier 2
   FitOpts O;
 };
 
@@ -306,7 +307,7 @@ constexpr int kFitStateDoubles = (int)((sizeof(FitState) + 15) / 16 * 2);
 __host__ __device__ inline size_t fit_seat_doubles(int kmax, int K, int nwarps, int cs, int max_insn,
                                                    int max_imm) {
   size_t d = kFitStateDoubles + (size_t)fit_workspace_doubles(kmax) + (size_t)cs * (K + 1) +
-             (size_t)nwarps * (K + 1) + kmax + 1 + max_imm + max_insn;
+             (size_t)nwarps * (K + 1) + kmax + 1 + max_imm + max_insn + 1;  // + pad word after END
   return (d + 1) & ~(size_t)1;  // 16-byte multiple
 }
 __host__ __device__ inline size_t fit_smem_bytes(int seats, int kmax, int K, int nwarps, int cs,
@@ -435,6 +436,10 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   bool drained = false;
   const bool timing = a.phase_cycles != nullptr && is_logic && lane == 0;
   long long t_logic = 0, t_seated = 0, n_pass = 0;
+  // cluster-level phases, seen by seat 0's lane 0 and charged to the runs of seat 0:
+  // [1] first barrier  [2] program/constant fetch  [4] sweeps + reductions  [5] second barrier
+  const bool ctiming = timing && seat == 0;
+  long long c_ph[4] = {0, 0, 0, 0}, c_t = 0;
   const double inv_n = 1.0 / (double)N;
 
   // every CTA of the cluster is running (and has its seat table initialised) before any DSMEM access
@@ -506,6 +511,11 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
             ph[0] += t_logic;
             ph[3] += (now - t_seated) - t_logic;
             ph[7] += n_pass;
+            if (ctiming) {
+              ph[1] += c_ph[0], ph[2] += c_ph[1], ph[4] += c_ph[2], ph[5] += c_ph[3];
+              ph[3] -= c_ph[0] + c_ph[1] + c_ph[2] + c_ph[3];
+              c_ph[0] = c_ph[1] = c_ph[2] = c_ph[3] = 0;
+            }
           }
         }
         __syncwarp();
@@ -519,7 +529,13 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
       }
       if (timing && my_prog >= 0) t_logic += clock64() - ta;
     }
+    if (ctiming) c_t = clock64();
     cluster.sync();  // requests (seat table, trial constants) are visible to every CTA
+    if (ctiming) {
+      const long long now = clock64();
+      c_ph[0] += now - c_t;
+      c_t = now;
+    }
 
     // ---- phase B: every CTA sweeps its slice for every occupied seat ----
     int active = 0;
@@ -551,6 +567,11 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
     }
     if (!active) break;  // no seated run and the queue is drained: uniform over the cluster
     __syncthreads();
+    if (ctiming) {
+      const long long now = clock64();
+      c_ph[1] += now - c_t;
+      c_t = now;
+    }
     for (int g = 0; g < G; ++g) {
       if (!((active >> g) & 1)) continue;
       double s, gsum[K > 0 ? K : 1];
@@ -566,7 +587,13 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
         for (int t = 0; t < K; ++t) r_cred[crank * (K + 1) + 1 + t] = gsum[t];
       }
     }
+    if (ctiming) {
+      const long long now = clock64();
+      c_ph[2] += now - c_t;
+      c_t = now;
+    }
     cluster.sync();  // every CTA's partial sums are in the leader's shared memory
+    if (ctiming) c_ph[3] += clock64() - c_t;
 
     // ---- phase C: responses, to every lane's private optimiser state ----
     if (is_logic && my_prog >= 0) {
