@@ -81,6 +81,7 @@ class _Lowering:
         self.sfu = 0
         self._need = {}
         self._tmask = {}
+        self._leaf = {}
 
     # ---- operands ----------------------------------------------------------------
     def imm(self, value):
@@ -94,7 +95,15 @@ class _Lowering:
         return self.imm_index[key]
 
     def leaf(self, node):
-        """(src, idx, tangent mask) if `node` is a leaf operand, else None."""
+        """(src, idx, tangent mask) if `node` is a leaf operand, else None (memoised: the
+        emitter asks several times per node and free_symbols walks the whole subtree)."""
+        try:
+            return self._leaf[node]
+        except KeyError:
+            r = self._leaf[node] = self._leaf_of(node)
+            return r
+
+    def _leaf_of(self, node):
         if isinstance(node, sp.Symbol):
             name = node.name
             if name in self.var_index:
