@@ -250,6 +250,9 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: device-resident steps ----
+    import gc
+    gc.collect()
+    gc.disable()   # a generation-2 collection over sympy's object graph stalls the host for ~50-100 ms
     for s in range(args.warmup):
         eng, x0d, rp, rs, _ = setups[s]
         eng.fit(rp, rs, x0d, opts)
@@ -271,6 +274,8 @@ def main():
     t_wall1 = time.time()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
+    if rank == 0:
+        print("step_ms " + " ".join(f"{b.name}:{m:.1f}" for b, m in zip(beams[args.warmup:], step_ms)), file=sys.stderr)
     launches = sum(s[0].launches for s in setups) - launches0
     fit_ms = fit_n = score_ms = 0.0
     for i in range(args.steps):
@@ -316,16 +321,21 @@ def main():
         vp = lambda a: a.ctypes.data_as(fitter.ctypes.c_void_p)  # noqa: E731
         eng._check(eng.lib.vsr_upload_points(eng._h, vp(Xc), vp(yh), Xc.shape[1], Xc.shape[1], Xc.shape[0],
                                              fitter.F64, st))
+        t1 = time.perf_counter()
         eng._check(eng.lib.vsr_upload_programs(eng._h, vp(insns), vp(insn_off), vp(imms), vp(imm_off), vp(ks), C, st))
+        t2 = time.perf_counter()
         o64 = fitter.default_opts(grad_mode=opts.grad_mode, eval_dtype=fitter.F64, score_dtype=fitter.F64,
                                   warps_per_run=args.warps)
         out = eng.fit_host(rp, rs, x0h, o64)
         dt = (time.perf_counter() - t0) * 1e3
         if i >= 0:
             e2e_ms += dt
+            if rank == 0:
+                print(f"e2e_ms {b.name}:{dt:.1f} (points {1e3 * (t1 - t0):.1f} programs {1e3 * (t2 - t1):.1f})", file=sys.stderr)
             h2d = Xc.nbytes + yh.nbytes + insns.nbytes + imms.nbytes + insn_off.nbytes + imm_off.nbytes + ks.nbytes + x0h.nbytes + rp.nbytes // 2 + rs.nbytes // 2
             d2h = sum(v.nbytes for v in out.values())
 
+    gc.enable()
     # ---- the Python entry point a driver calls: tokens in, dict out (sympy compile + fit +
     #      winner formatting), a few beams, cold compile cache ----
     api_ms, api_n = 0.0, 0

@@ -214,7 +214,7 @@ int next_pow2(int64_t v) {
 // long run is passes x latency per pass), and the slice fits the CTA's shared memory so the
 // points are read from HBM once per cluster.
 struct Geometry {
-  int cs, threads, stride, resident, seats;
+  int cs, threads, stride, resident, seats, banks, reserved;
   size_t smem;
 };
 
@@ -223,7 +223,7 @@ constexpr int kDefaultSeats = 4;            // runs in flight per cluster
 constexpr size_t kSmemBudget = (VSR_FIT_MINCTAS == 1 ? 200 : 100) * 1024;  // per CTA, so that all co-resident CTAs keep their slices
 
 Geometry choose_geometry(int64_t N, int P, int cap_threads, int forced_warps, int kmax, int K, int max_insn,
-                         int max_imm, int n_cols, int elem, int max_cluster, int seats) {
+                         int max_imm, int n_cols, int elem, int max_cluster, int seats, int want_banks) {
   Geometry g;
   const int64_t per_iter = (int64_t)cap_threads * P;
   int cs = 1;
@@ -233,13 +233,39 @@ Geometry choose_geometry(int64_t N, int P, int cap_threads, int forced_warps, in
   int threads = (int)std::min<int64_t>(cap_threads, ((per + P - 1) / P + 31) & ~(int64_t)31);
   if (forced_warps > 0) threads = std::min(cap_threads, 32 * forced_warps);
   threads = std::max(32, threads);
+  const int nw = threads / 32;
   g.cs = cs;
   g.threads = threads;
+  g.seats = std::max(1, std::min(std::min(seats, nw), (int)vsr::kMaxSeats));
+  // Slices: CTAs 1..cs-1 take `per` points, the leader the remainder.  When the cluster is big
+  // enough (cs >= 4, more than four warps) the remainder is sized for a leader that sweeps with
+  // two warps fewer: warps 0..1 of the leader are reserved for optimiser turns (in the two-bank
+  // schedule they run the optimisers of one half of the seats while everybody else sweeps the
+  // other half).  The layout and the set of sweeping warps are functions of (N, cs, threads)
+  // only, so a run's result does not depend on the number of seats or banks.
+  constexpr int kLeaderBusyWarps = 2;
+  g.banks = 1;
+  g.reserved = 0;
+  if (cs >= 4 && nw > 2 * kLeaderBusyWarps && forced_warps <= 0) {
+    const int64_t denom = (int64_t)(cs - 1) * nw + (nw - kLeaderBusyWarps);
+    int64_t per2 = (N * nw + denom - 1) / denom;
+    per2 = (per2 + 31) & ~(int64_t)31;
+    const int64_t lead = N - (int64_t)(cs - 1) * per2;
+    // accept only if nobody needs more tile iterations than with equal slices
+    const int64_t tile = (int64_t)threads * P, tile_lead = (int64_t)(nw - kLeaderBusyWarps) * 32 * P;
+    const int64_t it0 = (per + tile - 1) / tile;
+    const int64_t it_others = (per2 + tile - 1) / tile;
+    const int64_t it_lead = lead > 0 ? (lead + tile_lead - 1) / tile_lead : 0;
+    if (it_others <= it0 && it_lead <= it0 && lead <= per2) {
+      per = per2;
+      g.reserved = kLeaderBusyWarps;  // warps 0..1 of the leader run optimiser turns, never sweep
+      if (want_banks >= 2 && g.seats >= 2) g.banks = 2;
+    }
+  }
   g.stride = (int)per;
-  g.seats = std::max(1, std::min(std::min(seats, threads / 32), (int)vsr::kMaxSeats));
-  const size_t with = vsr::fit_smem_bytes(g.seats, kmax, K, threads / 32, cs, max_insn, max_imm, n_cols, (int)per, elem);
+  const size_t with = vsr::fit_smem_bytes(g.seats, kmax, K, nw, cs, max_insn, max_imm, n_cols, (int)per, elem);
   g.resident = with <= kSmemBudget && per < (1 << 30);
-  g.smem = g.resident ? with : vsr::fit_smem_bytes(g.seats, kmax, K, threads / 32, cs, max_insn, max_imm, -1, 0, elem);
+  g.smem = g.resident ? with : vsr::fit_smem_bytes(g.seats, kmax, K, nw, cs, max_insn, max_imm, -1, 0, elem);
   return g;
 }
 
@@ -354,10 +380,43 @@ int vsr_create(int device, vsr_handle** out) {
   if (prop.major != 10)
     return fail(nullptr, VSR_ECUDA, "device %d is sm_%d%d; libvsr is built for sm_100a only", device,
                 prop.major, prop.minor);
+  // Load every kernel instantiation now (CUDA loads modules lazily: the first launch of each of
+  // the 44 kernels would otherwise stall a fit by milliseconds), once per process and device.
+  static bool preloaded[64] = {false};
+  if (device < 64 && !preloaded[device]) {
+#define C(KK)                                                        \
+  if (e == cudaSuccess) e = vsr::preload_T<double, KK>();            \
+  if (e == cudaSuccess) e = vsr::preload_T<float, KK>();
+    C(0) C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(12) C(16)
+#undef C
+    if (e != cudaSuccess) return fail(nullptr, VSR_ECUDA, "loading the kernels: %s", cudaGetErrorString(e));
+    preloaded[device] = true;
+  }
   vsr_handle* h = new (std::nothrow) vsr_handle();
   if (!h) return fail(nullptr, VSR_ENOMEM, "out of host memory");
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
+  // scratch every fit needs, allocated here rather than inside the first fit: run lists (pinned
+  // + device), run counters, eval partials, the side streams and their events
+  e = h->h_lists.reserve(256 << 10);
+  if (e == cudaSuccess) e = h->d_lists.reserve(256 << 10);
+  if (e == cudaSuccess) e = h->d_queue.reserve(64 * sizeof(int32_t));
+  if (e == cudaSuccess) e = h->d_partial.reserve(1 << 20);
+  for (int i = 0; i < 12 && e == cudaSuccess; ++i) {
+    cudaStream_t s2;
+    e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+    if (e != cudaSuccess) break;
+    h->side_streams.push_back(s2);
+    cudaEvent_t e2;
+    e = cudaEventCreateWithFlags(&e2, cudaEventDisableTiming);
+    if (e == cudaSuccess) h->ev_join.push_back(e2);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    fail(nullptr, VSR_ECUDA, "allocating the handle's scratch: %s", cudaGetErrorString(e));
+    vsr_destroy(h);
+    return VSR_ECUDA;
+  }
   *out = h;
   return VSR_OK;
 }
@@ -725,9 +784,10 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
   // one run counter per group: the persistent clusters of a launch pull their runs from it
   VSR_CUDA(h, h->d_queue.reserve(groups.size() * sizeof(int32_t)));
   VSR_CUDA(h, cudaMemsetAsync(h->d_queue.p, 0, groups.size() * sizeof(int32_t), st));
-  // measurement hook: VSR_GEOMETRY="cluster:threads:seats" overrides the launch geometry
-  int hook_cluster = 0, hook_threads = 0, hook_seats = 0;
-  if (const char* env = getenv("VSR_GEOMETRY")) sscanf(env, "%d:%d:%d", &hook_cluster, &hook_threads, &hook_seats);
+  // measurement hook: VSR_GEOMETRY="cluster:threads:seats[:banks]" overrides the launch geometry
+  int hook_cluster = 0, hook_threads = 0, hook_seats = 0, hook_banks = 0;
+  if (const char* env = getenv("VSR_GEOMETRY"))
+    sscanf(env, "%d:%d:%d:%d", &hook_cluster, &hook_threads, &hook_seats, &hook_banks);
 
   // groups run concurrently: group 0 on the caller's stream, the others on side streams
   // forked from / joined to it with events
@@ -776,7 +836,8 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     int n_cols = 0;
     for (int j = 0; j < VSR_MAX_VARS; ++j) a.col_of_var[j] = ((g.var_mask >> j) & 1u) ? n_cols++ : -1;
     Geometry geo = choose_geometry(g.kmax == 0 ? 1 : ps.n, P, cap, opts->warps_per_run, g.kmax, g.K, g.max_insn,
-                                   g.max_imm, n_cols, elem, max_cluster, hook_seats > 0 ? hook_seats : kDefaultSeats);
+                                   g.max_imm, n_cols, elem, max_cluster, hook_seats > 0 ? hook_seats : kDefaultSeats,
+                                   hook_banks > 0 ? hook_banks : 2);
     if (g.kmax == 0) {  // runs without constants are only marked "not run": no points needed
       geo.resident = 0;
       geo.smem = vsr::fit_smem_bytes(geo.seats, g.kmax, g.K, geo.threads / 32, geo.cs, g.max_insn, g.max_imm, -1, 0, elem);
@@ -786,6 +847,8 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     a.tma_ok = tma_ok ? 1 : 0;
     a.slice_stride = geo.stride;
     a.seats = geo.seats;
+    a.banks = geo.banks;
+    a.reserved = geo.reserved;
     a.kmax = g.kmax;
     a.max_insn = g.max_insn;
     a.max_imm = g.max_imm;

@@ -47,6 +47,16 @@ cudaError_t launch_eval_T(const EvalArgs& a, int threads, size_t smem, cudaStrea
   return cudaGetLastError();
 }
 
+template <typename T, int K>
+cudaError_t preload_T() {
+  constexpr int P = points_per_thread(K);
+  cudaFuncAttributes attr;
+  cudaError_t e = cudaFuncGetAttributes(&attr, fit_kernel<T, K, P>);
+  if (e != cudaSuccess) return e;
+  return cudaFuncGetAttributes(&attr, eval_kernel<T, K, P>);
+}
+
+template cudaError_t preload_T<VSR_INST_T, VSR_INST_K>();
 template cudaError_t launch_fit_T<VSR_INST_T, VSR_INST_K>(const FitArgs&, int, int, size_t, int, cudaStream_t);
 template cudaError_t launch_eval_T<VSR_INST_T, VSR_INST_K>(const EvalArgs&, int, size_t, cudaStream_t);
 

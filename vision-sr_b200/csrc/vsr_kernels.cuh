@@ -61,6 +61,8 @@ struct FitArgs {
   int32_t tma_ok;        // 1: column starts and strides are 16-byte aligned (bulk copies)
   int32_t slice_stride;  // elements between columns of the staged slice
   int32_t seats;         // runs in flight per cluster (<= warps per CTA, <= kMaxSeats)
+  int32_t banks;         // 2: optimiser steps of one half of the seats overlap the sweeps of the other
+  int32_t reserved;      // warps of the leader CTA that never sweep (0 or 2), see choose_geometry
   int32_t kmax, max_insn, max_imm;  // maxima over this launch's programs (size the seat areas)
   int32_t n_cols;                   // columns of X this launch's programs read
   int32_t col_of_var[VSR_MAX_VARS]; // slice column of variable j (-1: unused)
@@ -108,12 +110,12 @@ template <typename T, int K, int P>
 __device__ __forceinline__ void sweep_points(const vsr_insn_t* prog, const double* imm,
                                              const T* cst, const T* __restrict__ X,
                                              const T* __restrict__ y, int64_t ldx, int64_t n0,
-                                             int64_t n1, double& s, double (&g)[K > 0 ? K : 1]) {
+                                             int64_t n1, double& s, double (&g)[K > 0 ? K : 1],
+                                             int tid, int nt) {
+  // tid / nt: index of this thread among the nt threads that take part in the sweep
   s = 0.0;
 #pragma unroll
   for (int t = 0; t < (K > 0 ? K : 1); ++t) g[t] = 0.0;
-  const int nt = blockDim.x;
-  const int tid = threadIdx.x;
   Stack<T, K, P> stk;
   GlobalPoints<T, P> xs;
   xs.X = X;
@@ -144,14 +146,19 @@ __device__ __forceinline__ void sweep_points(const vsr_insn_t* prog, const doubl
   }
 }
 
-// CTA-wide sum of (s, g[0..K)) into red[0..K]; red needs (nwarps)*(K+1) doubles.
-// After the call thread 0 holds the totals in s / g.  Fixed order: lane butterfly, then
-// warps 0..W-1.
+// named barrier over the `count` threads that take part in a sweep (count: multiple of 32)
+__device__ __forceinline__ void sweep_barrier(int count) {
+  asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory");
+}
+
+// Sum of (s, g[0..K)) over the `nw` warps that took part in a sweep, `warp` being this warp's
+// index among them; red needs nw*(K+1) doubles.  After the call lane 0 of warp 0 holds the totals
+// in s / g.  Fixed order: lane butterfly, then warps 0..nw-1.  Only the taking-part threads may
+// call it (named barrier, so that the optimiser warps of the leader CTA can stay out).
 template <int K>
-__device__ __forceinline__ void block_sum(double& s, double (&g)[K > 0 ? K : 1], double* red) {
+__device__ __forceinline__ void block_sum(double& s, double (&g)[K > 0 ? K : 1], double* red, int warp,
+                                          int nw) {
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int nw = (blockDim.x + 31) >> 5;
   s = warp_sum(s);
 #pragma unroll
   for (int t = 0; t < K; ++t) g[t] = warp_sum(g[t]);
@@ -161,10 +168,10 @@ __device__ __forceinline__ void block_sum(double& s, double (&g)[K > 0 ? K : 1],
 #pragma unroll
     for (int t = 0; t < K; ++t) red[warp * (K + 1) + 1 + t] = g[t];
   }
-  __syncthreads();
+  sweep_barrier(nw * 32);
   if (warp == 0) {
     // component `lane` summed over the warps in order 0..nw-1 (fixed order), then handed
-    // to thread 0
+    // to lane 0
     double acc = 0.0;
     if (lane <= K)
       for (int w = 0; w < nw; ++w) acc += red[w * (K + 1) + lane];
@@ -243,12 +250,10 @@ struct SlicePoints {
 template <typename T, int K, int P>
 __device__ __forceinline__ void sweep_slice(const vsr_insn_t* prog, const double* imm, const T* cst,
                                             const T* xs, const T* ys, int stride, int cnt, double& s,
-                                            double (&g)[K > 0 ? K : 1]) {
+                                            double (&g)[K > 0 ? K : 1], int tid, int nt) {
   s = 0.0;
 #pragma unroll
   for (int t = 0; t < (K > 0 ? K : 1); ++t) g[t] = 0.0;
-  const int nt = blockDim.x;
-  const int tid = threadIdx.x;
   Stack<T, K, P> stk;
   SlicePoints<T, P> src;
   src.base = xs;
@@ -340,11 +345,153 @@ __host__ __device__ constexpr int fit_min_ctas() {
 static __device__ __noinline__ int fit_step_call(FitState& S, const FitOpts& O) { return fit_step(S, O); }
 
 struct SeatCtrl {
-  int prog;   // program of the seated run, -1: seat empty
-  int k;      // its number of constants
-  int fresh;  // 1: the run was seated in this pass (every CTA must load its program)
-  int pad;
+  int prog;     // program of the seated run, -1: seat empty
+  int k;        // its number of constants
+  int fresh;    // 1: the run was seated in its optimiser's last turn (every CTA must load its program)
+  int drained;  // 1: the seat's optimiser found the launch's queue empty
 };
+
+// what the optimiser warp of a seat carries from one turn to the next (leader CTA only)
+struct SeatBook {
+  int slot;                     // output row of the seated run
+  int pad;
+  unsigned long long t0;        // TimedFun clock (bfgs.py:29-33)
+  double rf;                    // scratch: lane 0 -> all lanes
+  long long t_logic, t_seated, n_pass;  // phase_cycles bookkeeping
+};
+
+// One optimiser turn of seat `seat`, run by ONE warp of the leader CTA (any warp: all of the
+// seat's state is in shared memory): take in the totals of the sweep that served the seat's last
+// request, advance the run to its next request, and when it finishes write its results and seat
+// the next run of the launch's queue.  Publishes the seat table entry the sweepers read in the
+// next iteration.
+template <typename T, int K>
+__device__ __forceinline__ void seat_turn(const FitArgs& a, cooperative_groups::cluster_group& cluster, int seat,
+                                          int lane, int cs, FitState& S, double* ws, const double* cred,
+                                          SeatCtrl& ctrl, T* cst, SeatBook& book, int* s_drained) {
+  const bool timing = a.phase_cycles != nullptr && lane == 0;
+  long long ta = timing ? clock64() : 0;
+  int my_prog = ctrl.prog, my_k = ctrl.k;
+  if (my_prog >= 0) {
+    // component `lane` of (sum r^2, sum r df/dc_t) over the CTAs of the cluster in rank order;
+    // lane 0 applies the penalty rule, lanes 1..k scale the gradient
+    const double inv_n = 1.0 / (double)a.pts.n;
+    double tot = 0.0;
+    if (lane <= K)
+      for (int r = 0; r < cs; ++r) tot += cred[r * (K + 1) + lane];
+    const double f = a.O.loss_scale * (__shfl_sync(0xffffffffu, tot, 0) * inv_n);
+    bool bad = !isfinite(f);
+    if (a.O.stop_time < 1e8) {  // TimedFun: the clock starts at the first call
+      int late = 0;
+      if (lane == 0) {
+        const unsigned long long now = global_ns();
+        if (book.t0 == 0ull)
+          book.t0 = now;
+        else if ((double)(now - book.t0) * 1e-9 >= a.O.stop_time)
+          late = 1;
+      }
+      if (__shfl_sync(0xffffffffu, late, 0)) bad = true;
+    }
+    if (lane == 0) book.rf = bad ? a.O.penalty : f;
+    if (lane >= 1 && lane <= K && lane - 1 < my_k) {
+      const double gv = a.O.loss_scale * (2.0 * tot * inv_n);
+      S.rg[lane - 1] = (bad || !isfinite(gv)) ? 0.0 : gv;
+    }
+    __syncwarp();
+    S.rf = book.rf;
+    if (lane == 0) book.n_pass += 1;
+  }
+  int fresh = 0;
+  for (;;) {
+    if (my_prog < 0) {  // empty seat: take the next run of the launch
+      int r = -1;
+      if (!*s_drained) {
+        if (lane == 0) r = atomicAdd(a.queue, 1);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= a.n_runs) {
+          *s_drained = 1;  // every lane, same value
+          r = -1;
+        }
+      }
+      if (r < 0) break;
+      const int prog = a.run_prog[r];
+      const int slot = a.run_slot[r];
+      const int k = a.pt.k[prog];
+      if (k == 0) {  // nothing to optimise (reference bfgs.py:117-118)
+        if (lane == 0) {
+          int32_t* info = a.out_info + (int64_t)slot * 4;
+          info[0] = VSR_FIT_NOT_RUN;
+          info[1] = 0;
+          info[2] = 0;
+          info[3] = 0;
+          a.out_loss[slot] = 0.0;
+        }
+        continue;
+      }
+      my_prog = prog;
+      my_k = k;
+      fresh = 1;
+      fit_init(S, k, ws, a.x0 + (int64_t)slot * a.kstride);
+      if (lane == 0) {
+        book.slot = slot;
+        book.t0 = 0ull;
+        if (timing) book.t_seated = clock64(), book.t_logic = 0, book.n_pass = 0;
+      }
+      __syncwarp();
+    }
+    const int act = fit_step_call(S, a.O);
+    if (act == VSR_NEED_EVAL) break;
+    // finished: results out, seat free, try to seat another run in this same turn
+    __syncwarp();
+    if (lane == 0) {
+      const int slot = book.slot;
+      double* oc = a.out_consts + (int64_t)slot * a.kstride;
+      double* ol = a.out_lastx + (int64_t)slot * a.kstride;
+      for (int i = 0; i < my_k; ++i) {
+        oc[i] = S.xk[i];
+        ol[i] = S.lastx[i];
+      }
+      a.out_loss[slot] = S.old_fval;
+      int32_t* info = a.out_info + (int64_t)slot * 4;
+      info[0] = S.status;
+      info[1] = S.it;
+      info[2] = S.nfev;
+      info[3] = 0;
+      if (timing) {
+        const long long now = clock64();
+        book.t_logic += now - ta;
+        ta = now;
+        long long* ph = a.phase_cycles + (int64_t)slot * 8;
+        ph[0] += book.t_logic;
+        ph[3] += (now - book.t_seated) - book.t_logic;
+        ph[7] += book.n_pass;
+      }
+    }
+    __syncwarp();
+    my_prog = -1;
+    fresh = 0;
+  }
+  // Publish: the seat table entry and the trial constants go to EVERY CTA of the cluster as
+  // remote shared-memory stores (visible after the cluster barrier that ends the iteration), so
+  // that the sweepers never read remote memory on their critical path.  Nobody reads these
+  // locations during this iteration: the seat's bank is not the one being swept.
+  __syncwarp();
+  {
+    SeatCtrl v;
+    v.prog = my_prog;
+    v.k = my_k;
+    v.fresh = fresh;
+    v.drained = *s_drained;
+    for (int r = lane; r < cs; r += 32) *cluster.map_shared_rank(&ctrl, r) = v;
+    if (my_prog >= 0) {
+      for (int idx = lane; idx < cs * my_k; idx += 32) {
+        const int r = idx / my_k, i = idx - r * my_k;
+        cluster.map_shared_rank(cst, r)[i] = (T)S.xe[i];
+      }
+    }
+  }
+  if (timing && my_prog >= 0) book.t_logic += clock64() - ta;
+}
 
 template <typename T, int K, int P>
 __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>())) fit_kernel(const FitArgs a) {
@@ -352,8 +499,8 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) double smem[];
   __shared__ SeatCtrl s_ctrl[kMaxSeats];
-  __shared__ double s_rf[kMaxSeats];
-  __shared__ unsigned long long s_t0[kMaxSeats];
+  __shared__ SeatBook s_book[kMaxSeats];
+  __shared__ int s_drained;
   __shared__ __align__(8) uint64_t s_bar;
 
   const int cs = (int)cluster.num_blocks();
@@ -375,10 +522,13 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
 #define VSR_SEAT_INSN(g) (reinterpret_cast<vsr_insn_t*>(VSR_SEAT_IMM(g) + a.max_imm))
 
   // ---- this CTA's slice of the points ----
+  // CTAs 1..cs-1 take `per` points each, the leader (rank 0) takes what is left at the end: in
+  // the two-bank schedule two of its warps are busy with optimiser steps during every sweep, and
+  // the host sizes `per` so that the leader's remainder fits its remaining warps.
   const int64_t N = a.pts.n;
-  int64_t per = (N + cs - 1) / cs;
-  per = (per + 31) & ~(int64_t)31;  // slices start on 32-point boundaries (TMA alignment)
-  int64_t n0 = (int64_t)crank * per, n1 = n0 + per;
+  const int64_t per = a.slice_stride;
+  int64_t n0 = crank == 0 ? (int64_t)(cs - 1) * per : (int64_t)(crank - 1) * per;
+  int64_t n1 = crank == 0 ? N : n0 + per;
   n0 = n0 < N ? n0 : N;
   n1 = n1 < N ? n1 : N;
   const int cnt = (int)(n1 - n0);
@@ -422,213 +572,106 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
     s_ctrl[tid].prog = -1;
     s_ctrl[tid].k = 0;
     s_ctrl[tid].fresh = 0;
-    s_t0[tid] = 0ull;
+    s_ctrl[tid].drained = tid < G ? 0 : 1;
+    s_book[tid].t0 = 0ull;
+    s_book[tid].t_logic = s_book[tid].t_seated = s_book[tid].n_pass = 0;
   }
+  if (tid == 0) s_drained = 0;
   __syncthreads();
-
-  // ---- optimiser lanes: warp g of the leader CTA owns seat g ----
-  const bool is_logic = crank == 0 && warp < G;
-  const int seat = warp;
-  double* ws = VSR_SEAT_WS(is_logic ? seat : 0);
-  // warp g of the leader CTA runs the optimiser of seat g on the seat's shared state
-  FitState& S = *reinterpret_cast<FitState*>(VSR_SEAT_STATE(is_logic ? seat : 0));
-  int my_prog = -1, my_slot = -1, my_k = 0;  // the run in this warp's seat (logic warps only)
-  bool drained = false;
-  const bool timing = a.phase_cycles != nullptr && is_logic && lane == 0;
-  long long t_logic = 0, t_seated = 0, n_pass = 0;
-  // cluster-level phases, seen by seat 0's lane 0 and charged to the runs of seat 0:
-  // [1] first barrier  [2] program/constant fetch  [4] sweeps + reductions  [5] second barrier
-  const bool ctiming = timing && seat == 0;
-  long long c_ph[4] = {0, 0, 0, 0}, c_t = 0;
-  const double inv_n = 1.0 / (double)N;
 
   // every CTA of the cluster is running (and has its seat table initialised) before any DSMEM access
   cluster.sync();
-  const SeatCtrl* r_ctrl = cluster.map_shared_rank(s_ctrl, 0);
   double* r_smem = cluster.map_shared_rank(smem, 0);
 
-  for (;;) {
-    // ---- phase A: optimiser steps, one warp per seat, concurrently ----
-    if (is_logic) {
-      long long ta = timing ? clock64() : 0;
-      int fresh = 0;
-      for (;;) {
-        if (my_prog < 0) {  // empty seat: take the next run of the launch
-          int r = -1;
-          if (!drained) {
-            if (lane == 0) r = atomicAdd(a.queue, 1);
-            r = __shfl_sync(0xffffffffu, r, 0);
-            if (r >= a.n_runs) {
-              drained = true;
-              r = -1;
-            }
-          }
-          if (r < 0) break;
-          const int prog = a.run_prog[r];
-          const int slot = a.run_slot[r];
-          const int k = a.pt.k[prog];
-          if (k == 0) {  // nothing to optimise (reference bfgs.py:117-118)
-            if (lane == 0) {
-              int32_t* info = a.out_info + (int64_t)slot * 4;
-              info[0] = VSR_FIT_NOT_RUN;
-              info[1] = 0;
-              info[2] = 0;
-              info[3] = 0;
-              a.out_loss[slot] = 0.0;
-            }
-            continue;
-          }
-          my_prog = prog;
-          my_slot = slot;
-          my_k = k;
-          fresh = 1;
-          fit_init(S, k, ws, a.x0 + (int64_t)slot * a.kstride);
-          if (lane == 0) s_t0[seat] = 0ull;
-          if (timing) t_seated = clock64(), t_logic = 0, n_pass = 0;
-        }
-        const int act = fit_step_call(S, a.O);
-        if (act == VSR_NEED_EVAL) break;
-        // finished: results out, seat free, try to seat another run in this same pass
-        __syncwarp();
-        if (lane == 0) {
-          double* oc = a.out_consts + (int64_t)my_slot * a.kstride;
-          double* ol = a.out_lastx + (int64_t)my_slot * a.kstride;
-          for (int i = 0; i < my_k; ++i) {
-            oc[i] = S.xk[i];
-            ol[i] = S.lastx[i];
-          }
-          a.out_loss[my_slot] = S.old_fval;
-          int32_t* info = a.out_info + (int64_t)my_slot * 4;
-          info[0] = S.status;
-          info[1] = S.it;
-          info[2] = S.nfev;
-          info[3] = 0;
-          if (timing) {
-            const long long now = clock64();
-            t_logic += now - ta;
-            ta = now;
-            long long* ph = a.phase_cycles + (int64_t)my_slot * 8;
-            ph[0] += t_logic;
-            ph[3] += (now - t_seated) - t_logic;
-            ph[7] += n_pass;
-            if (ctiming) {
-              ph[1] += c_ph[0], ph[2] += c_ph[1], ph[4] += c_ph[2], ph[5] += c_ph[3];
-              ph[3] -= c_ph[0] + c_ph[1] + c_ph[2] + c_ph[3];
-              c_ph[0] = c_ph[1] = c_ph[2] = c_ph[3] = 0;
-            }
-          }
-        }
-        __syncwarp();
-        my_prog = -1;
-        fresh = 0;
+  // ---- the schedule ----
+  // Seats are split in banks (seat g -> bank g & 1; one bank when the cluster is too small to
+  // spare warps).  Iteration t SWEEPS the requests of bank t & 1, while the optimisers of the
+  // OTHER bank take in their previous sweep's totals and advance their runs to the next
+  // request.  One cluster barrier per iteration; a run advances one pass every two iterations,
+  // and with two banks the optimiser turns (16-21 k cycles of one warp each) are hidden behind
+  // the other bank's sweeps.
+  //
+  // Who does what in the leader CTA: when the slice layout reserves warps (a.reserved = 2, see
+  // choose_geometry) warps 0..1 NEVER sweep and run the optimiser turns (two banks: warp j takes
+  // seat lb + 2 j; one bank: warp j takes seats j, j + 2, ...), and the leader's slice is always
+  // swept by warps 2..nw-1, so the partition of the points over threads -- and with it the
+  // rounding of every sum -- does not depend on the number of seats or banks.  Without reserved
+  // warps (small clusters, one bank) warp g takes seat g and every warp sweeps.
+  const int n_banks = a.banks;  // 1 or 2
+  const int reserved = crank == 0 ? a.reserved : 0;
+  const bool may_logic = crank == 0 && (reserved > 0 ? warp < reserved : warp < G);
+  const bool sweeper = warp >= reserved;
+  const int swarp = warp - reserved, nsw = nw - reserved;
+  const int stid = swarp * 32 + lane, snt = nsw * 32;
+  bool prev_empty = false;
+  for (int t = 0;; ++t) {
+    const int sb = t & 1;   // bank swept now
+    const int lb = sb ^ 1;  // bank whose optimisers run now
+    if (may_logic && (n_banks == 2 || lb == 0)) {
+      // seats of bank lb this warp serves
+      const int first = reserved > 0 ? (n_banks == 2 ? lb + 2 * warp : warp) : warp;
+      const int step = reserved > 0 ? (n_banks == 2 ? 2 * reserved : reserved) : G;
+      for (int g = first; g < G; g += step) {
+        if (n_banks == 2 && (g & 1) != lb) continue;
+        seat_turn<T, K>(a, cluster, g, lane, cs, *reinterpret_cast<FitState*>(VSR_SEAT_STATE(g)), VSR_SEAT_WS(g),
+                        VSR_SEAT_CRED(g), s_ctrl[g], VSR_SEAT_CST(g), s_book[g], &s_drained);
       }
-      if (lane == 0) {
-        s_ctrl[seat].prog = my_prog;
-        s_ctrl[seat].k = my_k;
-        s_ctrl[seat].fresh = fresh;
-      }
-      if (timing && my_prog >= 0) t_logic += clock64() - ta;
-    }
-    if (ctiming) c_t = clock64();
-    cluster.sync();  // requests (seat table, trial constants) are visible to every CTA
-    if (ctiming) {
-      const long long now = clock64();
-      c_ph[0] += now - c_t;
-      c_t = now;
     }
 
-    // ---- phase B: every CTA sweeps its slice for every occupied seat ----
+    // ---- bank sb: seat table (this CTA's copy, published one iteration ago, stable now) ----
     int active = 0;
-    for (int g = 0; g < G; ++g) {
-      const SeatCtrl c = r_ctrl[g];
-      if (c.prog < 0) continue;
-      active |= 1 << g;
-      if (c.fresh) {
-        // the run was seated in this pass: its program into this CTA's seat area, VAR operands
-        // rewritten to slice columns, handler ids over the opcode bytes
-        const int i0 = a.pt.insn_off[c.prog], ni = a.pt.insn_off[c.prog + 1] - i0;
-        const int m0 = a.pt.imm_off[c.prog], nm = a.pt.imm_off[c.prog + 1] - m0;
-        vsr_insn_t* s_insn = VSR_SEAT_INSN(g);
-        double* s_imm = VSR_SEAT_IMM(g);
-        for (int i = tid; i < ni; i += blockDim.x) {
-          vsr_insn_t w = a.pt.insns[i0 + i];
-          const unsigned op = VSR_OP(w);
-          if (a.resident && op >= VSR_LOAD && op <= VSR_RPOW && op != VSR_PUSH && VSR_SRC(w) == VSR_SRC_VAR)
-            w = (w & ~((vsr_insn_t)0xffff << 16)) | ((vsr_insn_t)a.col_of_var[VSR_IDX(w)] << 16);
-          s_insn[i] = predecode(w);
-        }
-        for (int i = tid; i < nm; i += blockDim.x) s_imm[i] = a.pt.imms[m0 + i];
-      }
-      // trial constants from the leader's workspace (FitState.xe is its first k doubles), in
-      // the arithmetic type of the sweep
-      const double* r_xe = r_smem + (size_t)g * seat_d + kFitStateDoubles;
-      T* cst = VSR_SEAT_CST(g);
-      for (int i = tid; i < c.k; i += blockDim.x) cst[i] = (T)r_xe[i];
+    bool empty = true;
+    for (int g = n_banks == 2 ? sb : 0; g < G; g += n_banks) {
+      if (n_banks == 1 && sb == 1) break;  // single bank: odd iterations only run the optimisers
+      const SeatCtrl c = s_ctrl[g];
+      if (c.prog >= 0) active |= 1 << g;
+      if (c.prog >= 0 || !c.drained) empty = false;
     }
-    if (!active) break;  // no seated run and the queue is drained: uniform over the cluster
-    __syncthreads();
-    if (ctiming) {
-      const long long now = clock64();
-      c_ph[1] += now - c_t;
-      c_t = now;
-    }
-    for (int g = 0; g < G; ++g) {
-      if (!((active >> g) & 1)) continue;
-      double s, gsum[K > 0 ? K : 1];
-      if (a.resident)
-        sweep_slice<T, K, P>(VSR_SEAT_INSN(g), VSR_SEAT_IMM(g), VSR_SEAT_CST(g), xs, ys, stride, cnt, s, gsum);
-      else
-        sweep_points<T, K, P>(VSR_SEAT_INSN(g), VSR_SEAT_IMM(g), VSR_SEAT_CST(g), X, y, a.pts.ldx, n0, n1, s, gsum);
-      block_sum<K>(s, gsum, VSR_SEAT_RED(g));
-      if (tid == 0) {
-        double* r_cred = r_smem + (size_t)g * seat_d + kFitStateDoubles + wsd;
-        r_cred[crank * (K + 1)] = s;
-#pragma unroll
-        for (int t = 0; t < K; ++t) r_cred[crank * (K + 1) + 1 + t] = gsum[t];
-      }
-    }
-    if (ctiming) {
-      const long long now = clock64();
-      c_ph[2] += now - c_t;
-      c_t = now;
-    }
-    cluster.sync();  // every CTA's partial sums are in the leader's shared memory
-    if (ctiming) c_ph[3] += clock64() - c_t;
 
-    // ---- phase C: responses, to every lane's private optimiser state ----
-    if (is_logic && my_prog >= 0) {
-      const long long tc = timing ? clock64() : 0;
-      // component `lane` of (sum r^2, sum r df/dc_t) over the CTAs of the cluster in rank
-      // order; lane 0 applies the penalty rule, lanes 1..k scale the gradient
-      const double* cred = VSR_SEAT_CRED(seat);
-      double tot = 0.0;
-      if (lane <= K)
-        for (int r = 0; r < cs; ++r) tot += cred[r * (K + 1) + lane];
-      const double f = a.O.loss_scale * (__shfl_sync(0xffffffffu, tot, 0) * inv_n);
-      bool bad = !isfinite(f);
-      if (a.O.stop_time < 1e8) {  // TimedFun (bfgs.py:29-33): the clock starts at the first call
-        int late = 0;
-        if (lane == 0) {
-          const unsigned long long now = global_ns();
-          if (s_t0[seat] == 0ull)
-            s_t0[seat] = now;
-          else if ((double)(now - s_t0[seat]) * 1e-9 >= a.O.stop_time)
-            late = 1;
+    if (sweeper && active) {
+      for (int g = 0; g < G; ++g) {
+        if (!((active >> g) & 1)) continue;
+        const SeatCtrl c = s_ctrl[g];
+        if (c.fresh) {
+          // the run was seated one iteration ago: its program into this CTA's seat area, VAR
+          // operands rewritten to slice columns, handler ids over the opcode bytes
+          const int i0 = a.pt.insn_off[c.prog], ni = a.pt.insn_off[c.prog + 1] - i0;
+          const int m0 = a.pt.imm_off[c.prog], nm = a.pt.imm_off[c.prog + 1] - m0;
+          vsr_insn_t* s_insn = VSR_SEAT_INSN(g);
+          double* s_imm = VSR_SEAT_IMM(g);
+          for (int i = stid; i < ni; i += snt) {
+            vsr_insn_t w = a.pt.insns[i0 + i];
+            const unsigned op = VSR_OP(w);
+            if (a.resident && op >= VSR_LOAD && op <= VSR_RPOW && op != VSR_PUSH && VSR_SRC(w) == VSR_SRC_VAR)
+              w = (w & ~((vsr_insn_t)0xffff << 16)) | ((vsr_insn_t)a.col_of_var[VSR_IDX(w)] << 16);
+            s_insn[i] = predecode(w);
+          }
+          if (stid == 0) s_insn[ni] = 0;  // the pad word the interpreter prefetches
+          for (int i = stid; i < nm; i += snt) s_imm[i] = a.pt.imms[m0 + i];
         }
-        if (__shfl_sync(0xffffffffu, late, 0)) bad = true;
       }
-      if (lane == 0) s_rf[seat] = bad ? a.O.penalty : f;
-      if (lane >= 1 && lane <= K && lane - 1 < my_k) {
-        const double gv = a.O.loss_scale * (2.0 * tot * inv_n);
-        S.rg[lane - 1] = (bad || !isfinite(gv)) ? 0.0 : gv;
-      }
-      __syncwarp();
-      S.rf = s_rf[seat];
-      if (timing) {
-        t_logic += clock64() - tc;
-        n_pass += 1;
+      sweep_barrier(snt);
+      for (int g = 0; g < G; ++g) {
+        if (!((active >> g) & 1)) continue;
+        double s, gsum[K > 0 ? K : 1];
+        if (a.resident)
+          sweep_slice<T, K, P>(VSR_SEAT_INSN(g), VSR_SEAT_IMM(g), VSR_SEAT_CST(g), xs, ys, stride, cnt, s, gsum,
+                               stid, snt);
+        else
+          sweep_points<T, K, P>(VSR_SEAT_INSN(g), VSR_SEAT_IMM(g), VSR_SEAT_CST(g), X, y, a.pts.ldx, n0, n1, s,
+                                gsum, stid, snt);
+        block_sum<K>(s, gsum, VSR_SEAT_RED(g), swarp, nsw);
+        if (stid == 0) {
+          double* r_cred = r_smem + (size_t)g * seat_d + kFitStateDoubles + wsd;
+          r_cred[crank * (K + 1)] = s;
+#pragma unroll
+          for (int t2 = 0; t2 < K; ++t2) r_cred[crank * (K + 1) + 1 + t2] = gsum[t2];
+        }
       }
     }
+    cluster.sync();  // requests of bank lb and partial sums of bank sb are visible
+    if (empty && prev_empty) break;  // both banks empty, queue drained: uniform over the cluster
+    prev_empty = empty;
   }
 #undef VSR_SEAT_STATE
 #undef VSR_SEAT_WS
@@ -677,8 +720,9 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalArgs a) {
 
   double s, g[K > 0 ? K : 1];
   sweep_points<T, K, P>(s_insn, s_imm, cst, static_cast<const T*>(a.pts.X),
-                        static_cast<const T*>(a.pts.y), a.pts.ldx, n0, n1, s, g);
-  block_sum<K>(s, g, red);
+                        static_cast<const T*>(a.pts.y), a.pts.ldx, n0, n1, s, g, (int)threadIdx.x,
+                        (int)blockDim.x);
+  block_sum<K>(s, g, red, (int)(threadIdx.x >> 5), nw);
   if (threadIdx.x == 0) {
     double* out = a.partial + ((int64_t)pair * a.nsplit + split) * (K + 1);
     out[0] = s;
