@@ -314,14 +314,22 @@ VSR_HD void binary_apply(Dual<T, K> (&acc)[P], Stack<T, K, P>& stk, int& sp, uns
         break;
       case VSR_ADD:
         x.v += bv;
-        if (SRC == VSR_SRC_STACK || SRC == VSR_SRC_CONST) {
+        if (SRC == VSR_SRC_STACK) {  // only the operand's live tangents exist on the stack
+#pragma unroll
+          for (int i = 0; i < K; ++i)
+            if ((bm >> i) & 1u) x.d[i] += stk.s[sp][p][i + 1];
+        } else if (SRC == VSR_SRC_CONST) {
 #pragma unroll
           for (int i = 0; i < K; ++i) x.d[i] += VSR_TB(i);
         }
         break;
       case VSR_SUB:
         x.v -= bv;
-        if (SRC == VSR_SRC_STACK || SRC == VSR_SRC_CONST) {
+        if (SRC == VSR_SRC_STACK) {
+#pragma unroll
+          for (int i = 0; i < K; ++i)
+            if ((bm >> i) & 1u) x.d[i] -= stk.s[sp][p][i + 1];
+        } else if (SRC == VSR_SRC_CONST) {
 #pragma unroll
           for (int i = 0; i < K; ++i) x.d[i] -= VSR_TB(i);
         }
@@ -561,8 +569,12 @@ VSR_HD void eval_points(const vsr_insn_t* __restrict__ prog, const double* __res
         VSR_UCASE(VSR_TANH)
         VSR_UCASE(VSR_POWI)
 #undef VSR_UCASE
-      default:
+      default:  // predecode() only emits the ids above (programs are validated at upload)
+#if defined(__CUDA_ARCH__)
+        __builtin_unreachable();
+#else
         break;
+#endif
     }
   }
 }

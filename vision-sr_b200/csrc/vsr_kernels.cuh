@@ -139,7 +139,8 @@ __device__ __forceinline__ void sweep_points(const vsr_insn_t* prog, const doubl
         for (int t = 0; t < K; ++t) {
           const double gt = r * (double)acc[p].d[t];
           // a tangent that blew up where the value stayed finite (exp(-exp(x)) ...) counts 0
-          g[t] += isfinite(gt) ? gt : 0.0;
+          // (one compare and a predicated add; nan fails the compare)
+          if (fabs(gt) <= 1.7976931348623157e308) g[t] += gt;
         }
       }
     }
@@ -276,7 +277,7 @@ __device__ __forceinline__ void sweep_slice(const vsr_insn_t* prog, const double
 #pragma unroll
         for (int t = 0; t < K; ++t) {
           const double gt = r * (double)acc[p].d[t];
-          g[t] += isfinite(gt) ? gt : 0.0;
+          if (fabs(gt) <= 1.7976931348623157e308) g[t] += gt;
         }
       }
     }
@@ -308,11 +309,15 @@ __device__ __forceinline__ void sweep_slice(const vsr_insn_t* prog, const double
 // local variable it was evicted from L1 by every sweep's spill and operand-stack traffic, and
 // each pass re-read it from L2: 18-21 k cycles per optimiser step on an otherwise idle SM.
 constexpr int kFitStateDoubles = (int)((sizeof(FitState) + 15) / 16 * 2);
+// The code area of a seat is  cst[kSeatCstDoubles] | imm[VSR_MAX_IMMS] | insn[...]  with FIXED sizes
+// in front of the instructions, so that the interpreter addresses constants, literals and
+// instruction words at compile-time offsets from ONE register (see the sweep call sites).
+constexpr int kSeatCstDoubles = VSR_MAX_CONSTS + 2;
 
 __host__ __device__ inline size_t fit_seat_doubles(int kmax, int K, int nwarps, int cs, int max_insn,
                                                    int max_imm) {
   size_t d = kFitStateDoubles + (size_t)fit_workspace_doubles(kmax) + (size_t)cs * (K + 1) +
-             (size_t)nwarps * (K + 1) + kmax + 1 + max_imm + max_insn + 1;  // + pad word after END
+             (size_t)nwarps * (K + 1) + kSeatCstDoubles + VSR_MAX_IMMS + max_insn + 1;  // + pad word after END
   return (d + 1) & ~(size_t)1;  // 16-byte multiple
 }
 __host__ __device__ inline size_t fit_smem_bytes(int seats, int kmax, int K, int nwarps, int cs,
@@ -518,8 +523,8 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
 #define VSR_SEAT_CRED(g) (VSR_SEAT_WS(g) + wsd)
 #define VSR_SEAT_RED(g) (VSR_SEAT_CRED(g) + cs * (K + 1))
 #define VSR_SEAT_CST(g) (reinterpret_cast<T*>(VSR_SEAT_RED(g) + nw * (K + 1)))
-#define VSR_SEAT_IMM(g) (VSR_SEAT_RED(g) + nw * (K + 1) + a.kmax + 1)
-#define VSR_SEAT_INSN(g) (reinterpret_cast<vsr_insn_t*>(VSR_SEAT_IMM(g) + a.max_imm))
+#define VSR_SEAT_IMM(g) (VSR_SEAT_RED(g) + nw * (K + 1) + kSeatCstDoubles)
+#define VSR_SEAT_INSN(g) (reinterpret_cast<vsr_insn_t*>(VSR_SEAT_IMM(g) + VSR_MAX_IMMS))
 
   // ---- this CTA's slice of the points ----
   // CTAs 1..cs-1 take `per` points each, the leader (rank 0) takes what is left at the end: in
@@ -654,12 +659,19 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
       for (int g = 0; g < G; ++g) {
         if (!((active >> g) & 1)) continue;
         double s, gsum[K > 0 ? K : 1];
+        // the seat's code area through ONE opaque byte offset: without the asm the compiler
+        // re-derives the three pointers from (g, blockDim, kmax, ...) for every bytecode
+        // instruction -- 17 of the 36 instructions of the dispatch sequence -- instead of
+        // spending registers on them
+        unsigned code_off = (unsigned)(reinterpret_cast<char*>(VSR_SEAT_INSN(g)) - reinterpret_cast<char*>(smem));
+        asm volatile("" : "+r"(code_off));
+        const vsr_insn_t* c_insn = reinterpret_cast<const vsr_insn_t*>(reinterpret_cast<char*>(smem) + code_off);
+        const double* c_imm = reinterpret_cast<const double*>(c_insn) - VSR_MAX_IMMS;
+        const T* c_cst = reinterpret_cast<const T*>(c_imm - kSeatCstDoubles);
         if (a.resident)
-          sweep_slice<T, K, P>(VSR_SEAT_INSN(g), VSR_SEAT_IMM(g), VSR_SEAT_CST(g), xs, ys, stride, cnt, s, gsum,
-                               stid, snt);
+          sweep_slice<T, K, P>(c_insn, c_imm, c_cst, xs, ys, stride, cnt, s, gsum, stid, snt);
         else
-          sweep_points<T, K, P>(VSR_SEAT_INSN(g), VSR_SEAT_IMM(g), VSR_SEAT_CST(g), X, y, a.pts.ldx, n0, n1, s,
-                                gsum, stid, snt);
+          sweep_points<T, K, P>(c_insn, c_imm, c_cst, X, y, a.pts.ldx, n0, n1, s, gsum, stid, snt);
         block_sum<K>(s, gsum, VSR_SEAT_RED(g), swarp, nsw);
         if (stid == 0) {
           double* r_cred = r_smem + (size_t)g * seat_d + kFitStateDoubles + wsd;
