@@ -485,13 +485,8 @@ VSR_HD void eval_points(const vsr_insn_t* __restrict__ prog, const double* __res
 #pragma unroll
     for (int i = 0; i < (K > 0 ? K : 1); ++i) acc[p].d[i] = T(0);
   }
-  // the next word is fetched while the current handler runs (programs are followed by one
-  // readable pad word): the fetch -> decode -> indexed branch chain is the interpreter's
-  // critical path
-  vsr_insn_t wn = prog[0];
   for (int pc = 0;; ++pc) {
-    const vsr_insn_t w = wn;
-    wn = prog[pc + 1];
+    const vsr_insn_t w = prog[pc];
     const unsigned idx = VSR_IDX(w);
     const unsigned am = VSR_AMASK(w);
     const unsigned bm = VSR_BMASK(w);
