@@ -188,3 +188,37 @@ def test_config3_shape_many_restarts_two_variables(eng):
     np.testing.assert_allclose(res.lastx.cpu().numpy()[best, :3], [0.9, -0.35, 0.2], rtol=1e-5)
     # a quadratic bowl: every restart reaches it
     assert (fm < 1e-10).all()
+
+
+def test_widest_dual_kernel_and_fd_fallback_on_monomial_bases(eng):
+    """k = 14 constants use the widest dual kernel (K = 16); k = 18 exceeds it and falls back to
+    forward differences with the value-only kernel (vsr_fit's documented rule).  Both skeletons
+    are linear in their constants: closed-form least squares is the oracle."""
+    rng = np.random.RandomState(17)
+    N = 20_000
+    X = np.zeros((N, 10))
+    X[:, :3] = rng.uniform(-1.5, 1.5, size=(N, 3))
+    x1, x2, x3 = X[:, 0], X[:, 1], X[:, 2]
+    mono = [("1", np.ones(N)), ("x_1", x1), ("x_2", x2), ("x_3", x3), ("x_1*x_2", x1 * x2),
+            ("x_1*x_3", x1 * x3), ("x_2*x_3", x2 * x3), ("x_1**2", x1 ** 2), ("x_2**2", x2 ** 2),
+            ("x_3**2", x3 ** 2), ("x_1**3", x1 ** 3), ("x_2**3", x2 ** 3), ("x_3**3", x3 ** 3),
+            ("x_1*x_2*x_3", x1 * x2 * x3), ("x_1**2*x_2", x1 ** 2 * x2), ("x_2**2*x_3", x2 ** 2 * x3),
+            ("x_3**2*x_1", x3 ** 2 * x1), ("x_1**4", x1 ** 4)]
+    for k in (14, 18):
+        terms = mono[:k]
+        coef = rng.uniform(-2, 2, k)
+        A = np.stack([t[1] for t in terms], axis=1)
+        y = A @ coef + rng.normal(scale=0.01, size=N)
+        expr = " + ".join((f"c{j}" if t[0] == "1" else f"c{j}*{t[0]}") for j, t in enumerate(terms))
+        sol, *_ = np.linalg.lstsq(A, y, rcond=None)
+        eng.set_points(X, y, dtypes=(fitter.F64,), n_vars=3)
+        eng.set_programs([compile_skeleton(expr, k, VARS)])
+        x0 = np.random.RandomState(k).randn(2, k)
+        res = eng.fit([0, 0], [0, 1], x0)
+        c = res.consts.cpu().numpy()
+        info = res.info.cpu().numpy()
+        for r in range(2):
+            assert info[r, 0] in (0, 2), (k, info[r])
+            np.testing.assert_allclose(c[r, :k], sol, rtol=2e-3, atol=2e-4)
+        resid = y - A @ sol
+        assert res.final_mse.cpu().numpy().min() == pytest.approx(np.mean(resid * resid), rel=1e-5)
