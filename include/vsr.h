@@ -98,6 +98,17 @@ int vsr_eval(vsr_handle* h, const int32_t* prog_idx, const int32_t* const_row,
              int32_t n_pairs, const double* consts, int32_t kstride, int32_t dtype,
              double* out_loss, double* out_grad, void* stream);
 
+/* Driver-side scoring.  Replaces the block every driver runs after each fitfunc call
+ * (scripts/Feynman_test.py:81-97, and the same lines in the other *_test.py): re-lambdify the
+ * winner, predict on the FULL train / test set (1e5-1e6 rows), np.nan_to_num the prediction,
+ * r2_score it.  Same arguments as vsr_eval, value only:
+ *   out_mse[p] = mean_i (nan_to_num(f_{prog[p]}(x_i; consts[row[p]])) - y_i)^2
+ * with numpy's rule (nan -> 0, +-inf -> +-largest finite value of the dtype); the caller
+ * turns it into R^2 = 1 - out_mse / var(y) (src/visymre/scoring.py). */
+int vsr_score(vsr_handle* h, const int32_t* prog_idx, const int32_t* const_row,
+              int32_t n_pairs, const double* consts, int32_t kstride, int32_t dtype,
+              double* out_mse, void* stream);
+
 /* Multi-restart BFGS for n_runs (program, restart) runs; run r of the list fits program
  * run_prog[r] from x0[run_slot[r]] and writes every output at row run_slot[r]
  * (slots let a rank fit a shard of a C x R problem in place).  run_prog and run_slot

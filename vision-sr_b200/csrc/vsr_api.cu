@@ -292,7 +292,7 @@ int stage_lists(vsr_handle* h, const std::vector<int32_t>& all, cudaStream_t st)
 int run_eval_group(vsr_handle* h, int K, int dtype, const int32_t* d_prog, const int32_t* d_row,
                    const int32_t* d_out, int n_pairs, int kmax, int max_insn, int max_imm,
                    const double* consts, int kstride, double* out_loss, double* out_grad,
-                   cudaStream_t st) {
+                   cudaStream_t st, int nan_to_num = 0) {
   const PointSlot& ps = h->pts[dtype];
   const int P = points_per_thread(K);
   const int64_t N = ps.n;
@@ -316,6 +316,7 @@ int run_eval_group(vsr_handle* h, int K, int dtype, const int32_t* d_prog, const
   a.consts = consts;
   a.partial = (double*)h->d_partial.p;
   a.nsplit = nsplit;
+  a.nan_to_num = nan_to_num;
   const int nw = threads / 32;
   const size_t smem = sizeof(double) * (size_t)(nw * (K + 1) + kmax + 2 + max_imm + max_insn + 1);  // + pad word
   cudaError_t e = dtype == VSR_F64 ? launch_eval<double>(K, a, threads, smem, st)
@@ -678,6 +679,34 @@ int vsr_eval(vsr_handle* h, const int32_t* prog_idx, const int32_t* const_row, i
     // width-0 pairs (k == 0) have no gradient entries to write
   }
   return VSR_OK;
+}
+
+int vsr_score(vsr_handle* h, const int32_t* prog_idx, const int32_t* const_row, int32_t n_pairs,
+              const double* consts, int32_t kstride, int32_t dtype, double* out_mse, void* stream) {
+  int rc = check_ready(h, dtype);
+  if (rc) return rc;
+  if (!prog_idx || n_pairs <= 0 || !out_mse || kstride < 0 || (!consts && kstride > 0))
+    return fail(h, VSR_EINVAL, "bad score arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  VSR_CUDA(h, cudaSetDevice(h->device));
+  int kmax = 0, max_insn = 0, max_imm = 0;
+  std::vector<int32_t> all;
+  for (int p = 0; p < n_pairs; ++p) {
+    const int c = prog_idx[p];
+    if (c < 0 || c >= h->n_programs) return fail(h, VSR_EINVAL, "pair %d: program %d out of range", p, c);
+    if (h->h_k[c] > kstride) return fail(h, VSR_EINVAL, "pair %d: %d constants > kstride %d", p, h->h_k[c], kstride);
+    kmax = std::max(kmax, h->h_k[c]);
+    max_insn = std::max(max_insn, h->h_ninsn[c]);
+    max_imm = std::max(max_imm, h->h_nimm[c]);
+    all.push_back(c);
+  }
+  for (int p = 0; p < n_pairs; ++p) all.push_back(const_row ? const_row[p] : p);
+  for (int p = 0; p < n_pairs; ++p) all.push_back(p);
+  rc = stage_lists(h, all, st);
+  if (rc) return rc;
+  const int32_t* dl = (const int32_t*)h->d_lists.p;
+  return run_eval_group(h, 0, dtype, dl, dl + n_pairs, dl + 2 * n_pairs, n_pairs, kmax, max_insn, max_imm,
+                        consts, kstride, out_mse, nullptr, st, /*nan_to_num=*/1);
 }
 
 int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int32_t n_runs,

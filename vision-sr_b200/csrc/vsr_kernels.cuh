@@ -84,6 +84,7 @@ struct EvalArgs {
   const double* consts;
   double* partial;  // [n_pairs][nsplit][K+1]
   int32_t nsplit;
+  int32_t nan_to_num;  // 1: predictions pass through numpy's nan_to_num before the residual (vsr_score)
 };
 
 // ---- point source: coalesced global loads (read-only path) --------------------------
@@ -106,7 +107,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 // One pass over points [n0, n1): s += r^2, g[t] += r * d f/d c_t.
 // Every thread runs the same number of iterations (tail lanes are masked), so the
 // warp stays converged for the reduction that follows.
-template <typename T, int K, int P>
+// NTN: the prediction passes through numpy's nan_to_num (nan -> 0, +-inf -> +-largest finite
+// value of T) before the residual is taken: the drivers' scoring rule (Feynman_test.py:87).
+template <typename T, int K, int P, bool NTN = false>
 __device__ __forceinline__ void sweep_points(const vsr_insn_t* prog, const double* imm,
                                              const T* cst, const T* __restrict__ X,
                                              const T* __restrict__ y, int64_t ldx, int64_t n0,
@@ -133,7 +136,12 @@ __device__ __forceinline__ void sweep_points(const vsr_insn_t* prog, const doubl
 #pragma unroll
     for (int p = 0; p < P; ++p) {
       if (valid[p]) {
-        const double r = (double)acc[p].v - (double)__ldg(y + xs.idx[p]);
+        T pv = acc[p].v;
+        if (NTN) {
+          const T big = sizeof(T) == 8 ? (T)1.7976931348623157e308 : (T)3.4028234663852886e38;
+          pv = pv != pv ? T(0) : (pv > big ? big : (pv < -big ? -big : pv));
+        }
+        const double r = (double)pv - (double)__ldg(y + xs.idx[p]);
         s += r * r;
 #pragma unroll
         for (int t = 0; t < K; ++t) {
@@ -731,9 +739,14 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalArgs a) {
   n1 = n1 < N ? n1 : N;
 
   double s, g[K > 0 ? K : 1];
-  sweep_points<T, K, P>(s_insn, s_imm, cst, static_cast<const T*>(a.pts.X),
-                        static_cast<const T*>(a.pts.y), a.pts.ldx, n0, n1, s, g, (int)threadIdx.x,
-                        (int)blockDim.x);
+  if (K == 0 && a.nan_to_num)  // scoring rule of the drivers, value only
+    sweep_points<T, K, P, true>(s_insn, s_imm, cst, static_cast<const T*>(a.pts.X),
+                                static_cast<const T*>(a.pts.y), a.pts.ldx, n0, n1, s, g, (int)threadIdx.x,
+                                (int)blockDim.x);
+  else
+    sweep_points<T, K, P>(s_insn, s_imm, cst, static_cast<const T*>(a.pts.X),
+                          static_cast<const T*>(a.pts.y), a.pts.ldx, n0, n1, s, g, (int)threadIdx.x,
+                          (int)blockDim.x);
   block_sum<K>(s, g, red, (int)(threadIdx.x >> 5), nw);
   if (threadIdx.x == 0) {
     double* out = a.partial + ((int64_t)pair * a.nsplit + split) * (K + 1);

@@ -200,6 +200,28 @@ class Engine:
                                       self._stream()))
         return loss, g
 
+    def score(self, prog_idx, consts=None, dtype=F64, const_row=None):
+        """Driver-side scoring (``vsr_score``): mean squared error of every pair with the
+        prediction passed through numpy's ``nan_to_num`` first.  Returns a device tensor [n]."""
+        self.ensure_dtype(dtype)
+        prog_idx = np.ascontiguousarray(np.asarray(prog_idx, dtype=np.int32))
+        n = int(prog_idx.shape[0])
+        if consts is None:
+            consts = torch.zeros((n, 1), dtype=torch.float64, device=self.device)
+        consts = torch.as_tensor(consts, dtype=torch.float64, device=self.device)
+        if consts.dim() == 1:
+            consts = consts.reshape(n, -1)
+        consts = consts.contiguous()
+        rows = None
+        if const_row is not None:
+            rows = np.ascontiguousarray(np.asarray(const_row, dtype=np.int32))
+        out = torch.empty(n, dtype=torch.float64, device=self.device)
+        self._check(self.lib.vsr_score(self._h, _np_ptr(prog_idx),
+                                       _np_ptr(rows) if rows is not None else ctypes.c_void_p(0),
+                                       n, _ptr(consts), int(consts.shape[1]), dtype, _ptr(out),
+                                       self._stream()))
+        return out
+
     # ---- fitting ---------------------------------------------------------------------
     def fit(self, run_prog, run_slot, x0, opts=None, n_slots=None):
         """Multi-restart BFGS; ``x0`` is a device (or host) [n_slots, kstride] f64 tensor."""

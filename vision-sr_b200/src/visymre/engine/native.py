@@ -48,6 +48,8 @@ SIGNATURES = {
     "vsr_upload_programs": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, ctypes.c_int32, vp]),
     "vsr_eval": (ctypes.c_int, [vp, vp, vp, ctypes.c_int32, vp, ctypes.c_int32, ctypes.c_int32,
                                 vp, vp, vp]),
+    "vsr_score": (ctypes.c_int, [vp, vp, vp, ctypes.c_int32, vp, ctypes.c_int32, ctypes.c_int32,
+                                 vp, vp]),
     "vsr_fit": (ctypes.c_int, [vp, vp, vp, ctypes.c_int32, vp, ctypes.c_int32,
                                ctypes.POINTER(FitOpts), vp, vp, vp, vp, vp, vp]),
     "vsr_fit_host": (ctypes.c_int, [vp, vp, vp, ctypes.c_int32, ctypes.c_int32, vp,
