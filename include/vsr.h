@@ -134,6 +134,26 @@ int vsr_fit_host(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot
                  const vsr_fit_opts* opts, double* out_consts, double* out_lastx,
                  double* out_loss, double* out_final_mse, int32_t* out_info, void* stream);
 
+/* Constraint mask of the beam search.  Replaces the per-step, per-beam host
+ * loop of Model.fitfunc2 (src/visymre/architectures/model.py:385-411) and the Python stack walk
+ * _analyze_prefix_tree_context (model.py:522-560).  Token sets are bit masks over token ids
+ * (< 64); ids that do not exist are -1.
+ *   generated [beam][ld] int64 device: the beams' token ids, cur_len of them valid
+ *   beam_scores [beam] f32 device: beams below -1e8 get an all-zero row (model.py:387)
+ *   out_mask [beam][n_words] f32 device: 0 or -inf, to be ADDED to the log-probabilities
+ * Stateless: needs no handle. */
+typedef struct vsr_beam_rules {
+  uint64_t arity1, arity2;   /* unary / binary operator ids */
+  uint64_t transcendental;   /* model.py: transcendental_ids (no nesting of these) */
+  uint64_t all_ops;          /* forbidden once the open slots fill the remaining length */
+  uint64_t masked_vars;      /* variables absent from the data (model.py: masked_var_ids) */
+  int32_t pow_id, c_id, start_id, finish_id, pad_id;
+  int32_t length_eq;         /* cfg.length_eq */
+} vsr_beam_rules;
+int vsr_beam_mask(const int64_t* generated_dev, int64_t ld, int32_t beam, int32_t cur_len,
+                  const float* beam_scores_dev, const vsr_beam_rules* rules, int32_t n_words,
+                  float* out_mask_dev, void* stream);
+
 /* Number of kernels this handle has launched since creation (bench.py reports it). */
 int64_t vsr_launch_count(const vsr_handle* h);
 

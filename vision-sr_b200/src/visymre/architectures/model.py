@@ -131,3 +131,49 @@ def refine_hypotheses(hyps, X, y, cfg_params, test_data, x0=None, engine=None):
         "best_bfgs_loss": best_L,
         "best_token": best_tok,
     }
+
+
+def _bits(ids):
+    m = 0
+    for t in ids or ():
+        t = int(t)
+        if t < 0 or t >= 64:
+            raise ValueError(f"token id {t} outside the 64-bit mask of vsr_beam_mask")
+        m |= 1 << t
+    return m
+
+
+def beam_constraint_mask(generated, cur_len, beam_scores, n_words, *, arity_1_ids, arity_2_ids,
+                         transcendental_ids, all_op_ids, masked_var_ids, pow_id, c_id, start_id,
+                         finish_id, pad_id, length_eq):
+    """The "Constraint Logic" block of the beam search (model.py:382-411) as ONE device launch.
+
+    ``generated``: [beam, L] int64 CUDA tensor of token ids, the first ``cur_len`` valid;
+    ``beam_scores``: [beam] CUDA tensor.  Returns ``logit_mask`` [beam, n_words] float32 (0 or
+    -inf) to be added to the log-probabilities, computed without a host synchronisation: the
+    reference copies every beam to the host and walks it in Python at every decode step.
+    """
+    import ctypes
+    from ..engine import native
+    if not generated.is_cuda:
+        raise native.VsrError("beam_constraint_mask needs CUDA tensors (there is no CPU path)")
+    lib = native.load()
+    gen = generated.to(torch.int64).contiguous()
+    sc = beam_scores.to(torch.float32).contiguous()
+    beam = int(gen.shape[0])
+    out = torch.empty((beam, int(n_words)), dtype=torch.float32, device=gen.device)
+    r = native.BeamRules(arity1=_bits(arity_1_ids), arity2=_bits(arity_2_ids),
+                         transcendental=_bits(transcendental_ids), all_ops=_bits(all_op_ids),
+                         masked_vars=_bits([v for v in (masked_var_ids or ()) if int(v) < n_words]),
+                         pow_id=-1 if pow_id is None else int(pow_id),
+                         c_id=-1 if c_id is None else int(c_id), start_id=int(start_id),
+                         finish_id=-1 if finish_id is None else int(finish_id),
+                         pad_id=-1 if pad_id is None else int(pad_id), length_eq=int(length_eq))
+    with torch.cuda.device(gen.device):
+        st = torch.cuda.current_stream().cuda_stream
+        rc = lib.vsr_beam_mask(ctypes.c_void_p(gen.data_ptr()), int(gen.stride(0)), beam, int(cur_len),
+                               ctypes.c_void_p(sc.data_ptr()), ctypes.byref(r), int(n_words),
+                               ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(st))
+    if rc != 0:
+        raise native.VsrError(f"vsr_beam_mask failed ({rc})")
+    return out

@@ -34,6 +34,15 @@ class FitOpts(ctypes.Structure):
                 ("reserved", ctypes.c_int32)]
 
 
+class BeamRules(ctypes.Structure):
+    _fields_ = [("arity1", ctypes.c_uint64), ("arity2", ctypes.c_uint64),
+                ("transcendental", ctypes.c_uint64), ("all_ops", ctypes.c_uint64),
+                ("masked_vars", ctypes.c_uint64), ("pow_id", ctypes.c_int32),
+                ("c_id", ctypes.c_int32), ("start_id", ctypes.c_int32),
+                ("finish_id", ctypes.c_int32), ("pad_id", ctypes.c_int32),
+                ("length_eq", ctypes.c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/vsr.h one to one
 SIGNATURES = {
     "vsr_abi_version": (ctypes.c_int, []),
@@ -55,6 +64,8 @@ SIGNATURES = {
     "vsr_fit_host": (ctypes.c_int, [vp, vp, vp, ctypes.c_int32, ctypes.c_int32, vp,
                                     ctypes.c_int32, ctypes.POINTER(FitOpts), vp, vp, vp, vp, vp,
                                     vp]),
+    "vsr_beam_mask": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, vp,
+                                     ctypes.POINTER(BeamRules), ctypes.c_int32, vp, vp]),
     "vsr_launch_count": (ctypes.c_int64, [vp]),
     "vsr_set_profiling": (ctypes.c_int, [vp, ctypes.c_int32]),
     "vsr_read_profile": (ctypes.c_int, [vp, c_f64p]),
