@@ -251,3 +251,31 @@ def test_stop_time_zero_flattens_the_objective_like_timedfun(eng):
         ref = minimize(timed, x0[r], method="BFGS")
         assert loss[r] == pytest.approx(ref.fun, rel=1e-12)
         assert info[r, 1] == ref.nit and info[r, 2] == ref.nfev
+
+
+def test_duplicate_skeletons_are_fitted_once_when_asked(golden, test_data):
+    """with cfg.bfgs.collapse_duplicates, candidates that compile to the same
+    bytecode share one fit (from the first one's starting points) and keep their own skeleton."""
+    w2i = golden["word2id"]
+    cands = ["add c mul c x_1", "add mul c x_1 c", "add c mul c x_1", "mul c sin x_1"]
+    toks = [[w2i["S"]] + [w2i[w] for w in c.split()] + [w2i["F"]] for c in cands]
+    rng = np.random.RandomState(12)
+    N, R = 300, 3
+    X = np.zeros((1, N, 10))
+    X[0, :, 0] = rng.uniform(-2, 2, N)
+    y = 0.4 + 1.7 * X[0, :, 0]
+    Xt, yt = torch.tensor(X, device="cuda:0"), torch.tensor(y, device="cuda:0")
+    x0 = [rng.randn(R, 2) * 3, rng.randn(R, 2) * 3, rng.randn(R, 2) * 3, rng.randn(R, 1) * 3]
+    cfg = make_cfg(R, grad_mode="dual")
+    plain = vbfgs.bfgs_batch(toks, Xt, yt, cfg, test_data, x0=x0)
+    cfg.bfgs.collapse_duplicates = True
+    coll = vbfgs.bfgs_batch(toks, Xt, yt, cfg, test_data, x0=x0)
+    # the first of a group and candidates without a twin are untouched
+    assert coll[0][0] == plain[0][0] and float(coll[0][2]) == float(plain[0][2])
+    assert coll[3][0] == plain[3][0] and float(coll[3][2]) == float(plain[3][2])
+    # the exact twin shares the first one's fit; every candidate keeps its own skeleton string
+    assert coll[2][0] == coll[0][0] and float(coll[2][2]) == float(coll[0][2])
+    assert [c[3] for c in coll] == [p[3] for p in plain]
+    # all variants of the affine skeleton reach the exact fit either way
+    for c in coll[:3]:
+        assert float(c[2]) < 1e-12

@@ -135,6 +135,42 @@ def _compile_candidate(toks, cfg, test_data, variables):
 
 
 def bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
+    """Fit every candidate of a beam in one go (see ``_bfgs_batch``).
+
+    With ``cfg.bfgs.collapse_duplicates`` (off by default) candidates that
+    compile to the SAME bytecode -- beams that differ only in ways sympy canonicalises away,
+    ``model.py:459-483`` keeps them all -- are fitted once, from the starting points of the first
+    of them, and share the result; each keeps its own skeleton string.  The reference fits every
+    duplicate again from fresh random starting points, so this changes which restarts a
+    duplicate sees, not what a fit computes.
+    """
+    pred_strs = list(pred_strs)
+    if not _opt(cfg, "collapse_duplicates", False) or len(pred_strs) < 2:
+        return _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=x0, engine=engine)
+    variables = list(test_data.total_variables)
+    first, rep_of, own_expr = {}, [], []
+    for i, toks in enumerate(pred_strs):
+        try:
+            expr, k, prog = _compile_candidate(toks, cfg, test_data, variables)
+            key = (k, prog.insns.tobytes(), prog.imms.tobytes())
+        except Exception:  # noqa: BLE001 -- fails again, on its own, in _bfgs_batch
+            expr, key = None, ("error", i)
+        rep_of.append(first.setdefault(key, i))
+        own_expr.append(expr)
+    reps = sorted(set(rep_of))
+    pos = {r: j for j, r in enumerate(reps)}
+    sub = _bfgs_batch([pred_strs[r] for r in reps], X, y, cfg, test_data,
+                      x0=None if x0 is None else [x0[r] for r in reps], engine=engine)
+    out = []
+    for i, r in enumerate(rep_of):
+        res = sub[pos[r]]
+        if i != r and not isinstance(res, Exception):
+            res = (res[0], res[1], res[2], own_expr[i])
+        out.append(res)
+    return out
+
+
+def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
     """Fit every candidate of a beam in one go.
 
     Returns a list with one entry per candidate: the reference's 4-tuple
