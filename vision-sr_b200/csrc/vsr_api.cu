@@ -318,7 +318,7 @@ int run_eval_group(vsr_handle* h, int K, int dtype, const int32_t* d_prog, const
   a.nsplit = nsplit;
   a.nan_to_num = nan_to_num;
   const int nw = threads / 32;
-  const size_t smem = sizeof(double) * (size_t)(nw * (K + 1) + kmax + 2 + max_imm + max_insn + 1);  // + pad word
+  const size_t smem = sizeof(double) * (size_t)((K + 1) * threads + kmax + 2 + max_imm + max_insn + 1);  // + pad word
   cudaError_t e = dtype == VSR_F64 ? launch_eval<double>(K, a, threads, smem, st)
                                    : launch_eval<float>(K, a, threads, smem, st);
   if (e != cudaSuccess) return fail(h, VSR_ECUDA, "eval kernel launch failed: %s", cudaGetErrorString(e));

@@ -160,34 +160,29 @@ __device__ __forceinline__ void sweep_barrier(int count) {
   asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory");
 }
 
-// Sum of (s, g[0..K)) over the `nw` warps that took part in a sweep, `warp` being this warp's
-// index among them; red needs nw*(K+1) doubles.  After the call lane 0 of warp 0 holds the totals
-// in s / g.  Fixed order: lane butterfly, then warps 0..nw-1.  Only the taking-part threads may
-// call it (named barrier, so that the optimiser warps of the leader CTA can stay out).
+// Totals of (s, g[0..K)) over the `snt` threads that took part in a sweep, stored to out[0..K].
+// Every thread parks its partial sums in shared memory (scratch: [(K+1)][snt] doubles, column
+// per component), then component c is summed by warp c % nw: each lane adds its strided share in
+// index order, a lane butterfly finishes.  Fixed order, so results are reproducible and depend on
+// snt only.  4x fewer instructions than a butterfly over K+1 values in every warp followed by a
+// cross-warp stage (the shuffles were 7 % of the kernel's instructions).  Only the taking-part
+// threads may call it (named barrier, so the optimiser warps of the leader CTA can stay out).
 template <int K>
-__device__ __forceinline__ void block_sum(double& s, double (&g)[K > 0 ? K : 1], double* red, int warp,
-                                          int nw) {
-  const int lane = threadIdx.x & 31;
-  s = warp_sum(s);
+__device__ __forceinline__ void block_totals(double s, const double (&g)[K > 0 ? K : 1], double* scratch,
+                                             int stid, int snt, double* out) {
+  const int lane = stid & 31, warp = stid >> 5, nw = snt >> 5;
+  scratch[stid] = s;
 #pragma unroll
-  for (int t = 0; t < K; ++t) g[t] = warp_sum(g[t]);
-  if (nw == 1) return;
-  if (lane == 0) {
-    red[warp * (K + 1)] = s;
-#pragma unroll
-    for (int t = 0; t < K; ++t) red[warp * (K + 1) + 1 + t] = g[t];
-  }
-  sweep_barrier(nw * 32);
-  if (warp == 0) {
-    // component `lane` summed over the warps in order 0..nw-1 (fixed order), then handed
-    // to lane 0
+  for (int t = 0; t < K; ++t) scratch[(1 + t) * snt + stid] = g[t];
+  sweep_barrier(snt);
+  for (int c = warp; c <= K; c += nw) {
+    const double* col = scratch + c * snt;
     double acc = 0.0;
-    if (lane <= K)
-      for (int w = 0; w < nw; ++w) acc += red[w * (K + 1) + lane];
-    s = __shfl_sync(0xffffffffu, acc, 0);
-#pragma unroll
-    for (int t = 0; t < K; ++t) g[t] = __shfl_sync(0xffffffffu, acc, t + 1);
+    for (int j = lane; j < snt; j += 32) acc += col[j];
+    acc = warp_sum(acc);
+    if (lane == 0) out[c] = acc;
   }
+  sweep_barrier(snt);  // the scratch may be rewritten
 }
 
 // cooperative copy of one program into shared memory
@@ -310,8 +305,8 @@ __device__ __forceinline__ void sweep_slice(const vsr_insn_t* prog, const double
 // copies and stay there for every pass of every run the cluster handles.  Reduction order is
 // fixed (lanes, warps, CTA rank), so a run's result does not depend on its seat or cluster.
 //
-// dynamic shared memory (doubles):  per seat [ FitState | ws | cred[cs*(K+1)] | red[nw*(K+1)] | cst[kmax+1] |
-//   imm[max_imm] | insn[max_insn] ]  then the slice: (n_cols + 1) * stride * sizeof(T)
+// dynamic shared memory (doubles):  per seat [ FitState | ws | cred[cs*(K+1)] | cst | imm | insn ]
+//   then the reduction scratch [(K+1)][threads], then the slice: (n_cols + 1) * stride * sizeof(T)
 // The optimiser state of a seat lives in SHARED memory, one copy per seat that all 32 lanes of
 // the seat's warp read (broadcast) and write (same value, uniform control flow).  As a per-lane
 // local variable it was evicted from L1 by every sweep's spill and operand-stack traffic, and
@@ -325,13 +320,15 @@ constexpr int kSeatCstDoubles = VSR_MAX_CONSTS + 2;
 __host__ __device__ inline size_t fit_seat_doubles(int kmax, int K, int nwarps, int cs, int max_insn,
                                                    int max_imm) {
   size_t d = kFitStateDoubles + (size_t)fit_workspace_doubles(kmax) + (size_t)cs * (K + 1) +
-             (size_t)nwarps * (K + 1) + kSeatCstDoubles + VSR_MAX_IMMS + max_insn + 1;  // + pad word after END
+             kSeatCstDoubles + VSR_MAX_IMMS + max_insn + 1;  // + pad word after END
+  (void)nwarps;
   return (d + 1) & ~(size_t)1;  // 16-byte multiple
 }
 __host__ __device__ inline size_t fit_smem_bytes(int seats, int kmax, int K, int nwarps, int cs,
                                                  int max_insn, int max_imm, int n_cols, int stride,
                                                  int elem) {
   return (size_t)seats * fit_seat_doubles(kmax, K, nwarps, cs, max_insn, max_imm) * 8 +
+         (size_t)(K + 1) * nwarps * 32 * 8 +  // reduction scratch of block_totals
          (n_cols >= 0 ? (size_t)(n_cols + 1) * stride * elem : 0);
 }
 
@@ -529,9 +526,8 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
 #define VSR_SEAT_STATE(g) (smem + (size_t)(g)*seat_d)
 #define VSR_SEAT_WS(g) (VSR_SEAT_STATE(g) + kFitStateDoubles)
 #define VSR_SEAT_CRED(g) (VSR_SEAT_WS(g) + wsd)
-#define VSR_SEAT_RED(g) (VSR_SEAT_CRED(g) + cs * (K + 1))
-#define VSR_SEAT_CST(g) (reinterpret_cast<T*>(VSR_SEAT_RED(g) + nw * (K + 1)))
-#define VSR_SEAT_IMM(g) (VSR_SEAT_RED(g) + nw * (K + 1) + kSeatCstDoubles)
+#define VSR_SEAT_CST(g) (reinterpret_cast<T*>(VSR_SEAT_CRED(g) + cs * (K + 1)))
+#define VSR_SEAT_IMM(g) (VSR_SEAT_CRED(g) + cs * (K + 1) + kSeatCstDoubles)
 #define VSR_SEAT_INSN(g) (reinterpret_cast<vsr_insn_t*>(VSR_SEAT_IMM(g) + VSR_MAX_IMMS))
 
   // ---- this CTA's slice of the points ----
@@ -552,7 +548,7 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   T* ys = nullptr;
   const int stride = a.slice_stride;
   if (a.resident) {
-    ys = reinterpret_cast<T*>(smem + (size_t)G * seat_d);
+    ys = reinterpret_cast<T*>(smem + (size_t)G * seat_d + (size_t)(K + 1) * blockDim.x);
     xs = ys + stride;
     constexpr int kAlign = 16 / (int)sizeof(T);
     const int full = cnt & ~(kAlign - 1);  // elements per column that move as 16-byte units
@@ -680,13 +676,8 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
           sweep_slice<T, K, P>(c_insn, c_imm, c_cst, xs, ys, stride, cnt, s, gsum, stid, snt);
         else
           sweep_points<T, K, P>(c_insn, c_imm, c_cst, X, y, a.pts.ldx, n0, n1, s, gsum, stid, snt);
-        block_sum<K>(s, gsum, VSR_SEAT_RED(g), swarp, nsw);
-        if (stid == 0) {
-          double* r_cred = r_smem + (size_t)g * seat_d + kFitStateDoubles + wsd;
-          r_cred[crank * (K + 1)] = s;
-#pragma unroll
-          for (int t2 = 0; t2 < K; ++t2) r_cred[crank * (K + 1) + 1 + t2] = gsum[t2];
-        }
+        block_totals<K>(s, gsum, smem + (size_t)G * seat_d, stid, snt,
+                        r_smem + (size_t)g * seat_d + kFitStateDoubles + wsd + crank * (K + 1));
       }
     }
     cluster.sync();  // requests of bank lb and partial sums of bank sb are visible
@@ -696,7 +687,6 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
 #undef VSR_SEAT_STATE
 #undef VSR_SEAT_WS
 #undef VSR_SEAT_CRED
-#undef VSR_SEAT_RED
 #undef VSR_SEAT_CST
 #undef VSR_SEAT_IMM
 #undef VSR_SEAT_INSN
@@ -704,7 +694,7 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   cluster.sync();
 }
 
-// dynamic shared memory of eval_kernel, in doubles: red | cst[k] | imm | insn
+// dynamic shared memory of eval_kernel, in doubles: red[(K+1)*threads] | cst[k] | imm | insn
 template <typename T, int K, int P>
 __global__ void __launch_bounds__(256) eval_kernel(const EvalArgs a) {
   extern __shared__ double smem[];
@@ -714,9 +704,10 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalArgs a) {
   const int prog = a.pair_prog[pair];
   const int k = a.pt.k[prog];
   const int nw = (blockDim.x + 31) >> 5;
-  double* red = smem;
-  T* cst = reinterpret_cast<T*>(red + nw * (K + 1));
-  double* s_imm = red + nw * (K + 1) + k + 1;
+  double* red = smem;  // reduction scratch of block_totals: [(K+1)][blockDim.x]
+  const int n_red = (K + 1) * (int)blockDim.x;
+  T* cst = reinterpret_cast<T*>(red + n_red);
+  double* s_imm = red + n_red + k + 1;
   const int m_imm = a.pt.imm_off[prog + 1] - a.pt.imm_off[prog];
   vsr_insn_t* s_insn = reinterpret_cast<vsr_insn_t*>(s_imm + m_imm);
   int n_insn, n_imm;
@@ -747,13 +738,8 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalArgs a) {
     sweep_points<T, K, P>(s_insn, s_imm, cst, static_cast<const T*>(a.pts.X),
                           static_cast<const T*>(a.pts.y), a.pts.ldx, n0, n1, s, g, (int)threadIdx.x,
                           (int)blockDim.x);
-  block_sum<K>(s, g, red, (int)(threadIdx.x >> 5), nw);
-  if (threadIdx.x == 0) {
-    double* out = a.partial + ((int64_t)pair * a.nsplit + split) * (K + 1);
-    out[0] = s;
-#pragma unroll
-    for (int t = 0; t < K; ++t) out[1 + t] = g[t];
-  }
+  block_totals<K>(s, g, red, (int)threadIdx.x, (int)blockDim.x,
+                  a.partial + ((int64_t)pair * a.nsplit + split) * (K + 1));
 }
 
 #if defined(VSR_API_TU)  // plain kernels: defined once, in the API translation unit
