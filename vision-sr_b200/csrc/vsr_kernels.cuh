@@ -104,25 +104,29 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// One pass over points [n0, n1): s += r^2, g[t] += r * d f/d c_t.
-// Every thread runs the same number of iterations (tail lanes are masked), so the
-// warp stays converged for the reduction that follows.
+// keeps a value in a register: without it the compiler re-derives point indices and thread
+// ranks from %tid inside every handler that needs them (it rematerialises rather than spend one
+// of the 96 registers)
+__device__ __forceinline__ void keep_in_register(int& v) { asm volatile("" : "+r"(v)); }
+
+// One pass over points [n0, n1).  The thread's partial sums  sum r^2  and  sum r * d f/d c_t  go
+// straight into its slots of the reduction scratch ([(K+1)][nt] doubles, see block_totals): no
+// accumulator is live across the interpreter (they used to be spilled around it).
+// Every thread runs the same number of iterations (tail lanes are masked), so the warp stays
+// converged for the reduction that follows.
 // NTN: the prediction passes through numpy's nan_to_num (nan -> 0, +-inf -> +-largest finite
 // value of T) before the residual is taken: the drivers' scoring rule (Feynman_test.py:87).
 template <typename T, int K, int P, bool NTN = false>
 __device__ __forceinline__ void sweep_points(const vsr_insn_t* prog, const double* imm,
                                              const T* cst, const T* __restrict__ X,
                                              const T* __restrict__ y, int64_t ldx, int64_t n0,
-                                             int64_t n1, double& s, double (&g)[K > 0 ? K : 1],
-                                             int tid, int nt) {
+                                             int64_t n1, double* scratch, int tid, int nt) {
   // tid / nt: index of this thread among the nt threads that take part in the sweep
-  s = 0.0;
-#pragma unroll
-  for (int t = 0; t < (K > 0 ? K : 1); ++t) g[t] = 0.0;
   Stack<T, K, P> stk;
   GlobalPoints<T, P> xs;
   xs.X = X;
   xs.ldx = ldx;
+  bool first = true;
   for (int64_t base = n0; base < n1; base += (int64_t)nt * P) {
     bool valid[P];
 #pragma unroll
@@ -133,6 +137,9 @@ __device__ __forceinline__ void sweep_points(const vsr_insn_t* prog, const doubl
     }
     Dual<T, K> acc[P];
     eval_points<T, K, P>(prog, imm, cst, xs, acc, stk);
+    double ps = 0.0, pg[K > 0 ? K : 1];
+#pragma unroll
+    for (int t = 0; t < (K > 0 ? K : 1); ++t) pg[t] = 0.0;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
       if (valid[p]) {
@@ -142,16 +149,31 @@ __device__ __forceinline__ void sweep_points(const vsr_insn_t* prog, const doubl
           pv = pv != pv ? T(0) : (pv > big ? big : (pv < -big ? -big : pv));
         }
         const double r = (double)pv - (double)__ldg(y + xs.idx[p]);
-        s += r * r;
+        ps += r * r;
 #pragma unroll
         for (int t = 0; t < K; ++t) {
           const double gt = r * (double)acc[p].d[t];
           // a tangent that blew up where the value stayed finite (exp(-exp(x)) ...) counts 0
           // (one compare and a predicated add; nan fails the compare)
-          if (fabs(gt) <= 1.7976931348623157e308) g[t] += gt;
+          if (fabs(gt) <= 1.7976931348623157e308) pg[t] += gt;
         }
       }
     }
+    if (first) {
+      scratch[tid] = ps;
+#pragma unroll
+      for (int t = 0; t < K; ++t) scratch[(1 + t) * nt + tid] = pg[t];
+      first = false;
+    } else {
+      scratch[tid] += ps;
+#pragma unroll
+      for (int t = 0; t < K; ++t) scratch[(1 + t) * nt + tid] += pg[t];
+    }
+  }
+  if (first) {  // no points at all
+    scratch[tid] = 0.0;
+#pragma unroll
+    for (int t = 0; t < K; ++t) scratch[(1 + t) * nt + tid] = 0.0;
   }
 }
 
@@ -160,21 +182,17 @@ __device__ __forceinline__ void sweep_barrier(int count) {
   asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory");
 }
 
-// Totals of (s, g[0..K)) over the `snt` threads that took part in a sweep, stored to out[0..K].
-// Every thread parks its partial sums in shared memory (scratch: [(K+1)][snt] doubles, column
-// per component), then component c is summed by warp c % nw: each lane adds its strided share in
+// Totals of (sum r^2, sum r df/dc_t) over the `snt` threads that took part in a sweep, stored to
+// out[0..K].  The sweep parked every thread's partial sums in shared memory (scratch:
+// [(K+1)][snt] doubles, column per component); component c is summed by warp c % nw: each lane adds its strided share in
 // index order, a lane butterfly finishes.  Fixed order, so results are reproducible and depend on
 // snt only.  4x fewer instructions than a butterfly over K+1 values in every warp followed by a
 // cross-warp stage (the shuffles were 7 % of the kernel's instructions).  Only the taking-part
 // threads may call it (named barrier, so the optimiser warps of the leader CTA can stay out).
 template <int K>
-__device__ __forceinline__ void block_totals(double s, const double (&g)[K > 0 ? K : 1], double* scratch,
-                                             int stid, int snt, double* out) {
+__device__ __forceinline__ void block_totals(double* scratch, int stid, int snt, double* out) {
   const int lane = stid & 31, warp = stid >> 5, nw = snt >> 5;
-  scratch[stid] = s;
-#pragma unroll
-  for (int t = 0; t < K; ++t) scratch[(1 + t) * snt + stid] = g[t];
-  sweep_barrier(snt);
+  sweep_barrier(snt);  // every thread's partial sums are parked (by the sweep)
   for (int c = warp; c <= K; c += nw) {
     const double* col = scratch + c * snt;
     double acc = 0.0;
@@ -250,18 +268,16 @@ struct SlicePoints {
   __device__ __forceinline__ T col(unsigned j, int p) const { return base[j * stride + idx[p]]; }
 };
 
-// One pass over the resident slice (cnt points): s += r^2, g[t] += r * d f/d c_t.
+// One pass over the resident slice (cnt points); partial sums parked like sweep_points does.
 template <typename T, int K, int P>
 __device__ __forceinline__ void sweep_slice(const vsr_insn_t* prog, const double* imm, const T* cst,
-                                            const T* xs, const T* ys, int stride, int cnt, double& s,
-                                            double (&g)[K > 0 ? K : 1], int tid, int nt) {
-  s = 0.0;
-#pragma unroll
-  for (int t = 0; t < (K > 0 ? K : 1); ++t) g[t] = 0.0;
+                                            const T* xs, const T* ys, int stride, int cnt, double* scratch,
+                                            int tid, int nt) {
   Stack<T, K, P> stk;
   SlicePoints<T, P> src;
   src.base = xs;
   src.stride = stride;
+  bool first = true;
   for (int base = 0; base < cnt; base += nt * P) {
     bool valid[P];
 #pragma unroll
@@ -269,21 +285,40 @@ __device__ __forceinline__ void sweep_slice(const vsr_insn_t* prog, const double
       const int i = base + p * nt + tid;
       valid[p] = i < cnt;
       src.idx[p] = valid[p] ? i : (cnt - 1);
+      keep_in_register(src.idx[p]);
     }
     Dual<T, K> acc[P];
     eval_points<T, K, P>(prog, imm, cst, src, acc, stk);
+    double ps = 0.0, pg[K > 0 ? K : 1];
+#pragma unroll
+    for (int t = 0; t < (K > 0 ? K : 1); ++t) pg[t] = 0.0;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-      if (valid[p]) {
+      if (src.idx[p] == base + p * nt + tid) {  // valid[p], from the kept index
         const double r = (double)acc[p].v - (double)ys[src.idx[p]];
-        s += r * r;
+        ps += r * r;
 #pragma unroll
         for (int t = 0; t < K; ++t) {
           const double gt = r * (double)acc[p].d[t];
-          if (fabs(gt) <= 1.7976931348623157e308) g[t] += gt;
+          if (fabs(gt) <= 1.7976931348623157e308) pg[t] += gt;
         }
       }
     }
+    if (first) {
+      scratch[tid] = ps;
+#pragma unroll
+      for (int t = 0; t < K; ++t) scratch[(1 + t) * nt + tid] = pg[t];
+      first = false;
+    } else {
+      scratch[tid] += ps;
+#pragma unroll
+      for (int t = 0; t < K; ++t) scratch[(1 + t) * nt + tid] += pg[t];
+    }
+  }
+  if (first) {  // no points in this CTA's slice
+    scratch[tid] = 0.0;
+#pragma unroll
+    for (int t = 0; t < K; ++t) scratch[(1 + t) * nt + tid] = 0.0;
   }
 }
 
@@ -611,7 +646,9 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   const bool may_logic = crank == 0 && (reserved > 0 ? warp < reserved : warp < G);
   const bool sweeper = warp >= reserved;
   const int swarp = warp - reserved, nsw = nw - reserved;
-  const int stid = swarp * 32 + lane, snt = nsw * 32;
+  int stid = swarp * 32 + lane, snt = nsw * 32;
+  keep_in_register(stid);
+  keep_in_register(snt);
   bool prev_empty = false;
   for (int t = 0;; ++t) {
     const int sb = t & 1;   // bank swept now
@@ -662,7 +699,6 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
       sweep_barrier(snt);
       for (int g = 0; g < G; ++g) {
         if (!((active >> g) & 1)) continue;
-        double s, gsum[K > 0 ? K : 1];
         // the seat's code area through ONE opaque byte offset: without the asm the compiler
         // re-derives the three pointers from (g, blockDim, kmax, ...) for every bytecode
         // instruction -- 17 of the 36 instructions of the dispatch sequence -- instead of
@@ -672,11 +708,12 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
         const vsr_insn_t* c_insn = reinterpret_cast<const vsr_insn_t*>(reinterpret_cast<char*>(smem) + code_off);
         const double* c_imm = reinterpret_cast<const double*>(c_insn) - VSR_MAX_IMMS;
         const T* c_cst = reinterpret_cast<const T*>(c_imm - kSeatCstDoubles);
+        double* scratch = smem + (size_t)G * seat_d;
         if (a.resident)
-          sweep_slice<T, K, P>(c_insn, c_imm, c_cst, xs, ys, stride, cnt, s, gsum, stid, snt);
+          sweep_slice<T, K, P>(c_insn, c_imm, c_cst, xs, ys, stride, cnt, scratch, stid, snt);
         else
-          sweep_points<T, K, P>(c_insn, c_imm, c_cst, X, y, a.pts.ldx, n0, n1, s, gsum, stid, snt);
-        block_totals<K>(s, gsum, smem + (size_t)G * seat_d, stid, snt,
+          sweep_points<T, K, P>(c_insn, c_imm, c_cst, X, y, a.pts.ldx, n0, n1, scratch, stid, snt);
+        block_totals<K>(scratch, stid, snt,
                         r_smem + (size_t)g * seat_d + kFitStateDoubles + wsd + crank * (K + 1));
       }
     }
@@ -729,16 +766,15 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalArgs a) {
   n0 = n0 < N ? n0 : N;
   n1 = n1 < N ? n1 : N;
 
-  double s, g[K > 0 ? K : 1];
   if (K == 0 && a.nan_to_num)  // scoring rule of the drivers, value only
     sweep_points<T, K, P, true>(s_insn, s_imm, cst, static_cast<const T*>(a.pts.X),
-                                static_cast<const T*>(a.pts.y), a.pts.ldx, n0, n1, s, g, (int)threadIdx.x,
+                                static_cast<const T*>(a.pts.y), a.pts.ldx, n0, n1, red, (int)threadIdx.x,
                                 (int)blockDim.x);
   else
     sweep_points<T, K, P>(s_insn, s_imm, cst, static_cast<const T*>(a.pts.X),
-                          static_cast<const T*>(a.pts.y), a.pts.ldx, n0, n1, s, g, (int)threadIdx.x,
+                          static_cast<const T*>(a.pts.y), a.pts.ldx, n0, n1, red, (int)threadIdx.x,
                           (int)blockDim.x);
-  block_totals<K>(s, g, red, (int)threadIdx.x, (int)blockDim.x,
+  block_totals<K>(red, (int)threadIdx.x, (int)blockDim.x,
                   a.partial + ((int64_t)pair * a.nsplit + split) * (K + 1));
 }
 
