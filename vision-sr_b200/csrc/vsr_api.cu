@@ -878,6 +878,14 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     a.seats = geo.seats;
     a.banks = geo.banks;
     a.reserved = geo.reserved;
+    {
+      const vsr::SeatLayout L = vsr::fit_seat_layout(g.kmax, g.K, geo.threads / 32, geo.cs, g.max_insn, g.max_imm);
+      a.seat_d = L.seat_d;
+      a.off_cred = L.off_cred;
+      a.off_cst = L.off_cst;
+      a.off_imm = L.off_imm;
+      a.off_insn = L.off_insn;
+    }
     a.kmax = g.kmax;
     a.max_insn = g.max_insn;
     a.max_imm = g.max_imm;

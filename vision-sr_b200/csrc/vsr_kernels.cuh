@@ -63,6 +63,9 @@ struct FitArgs {
   int32_t seats;         // runs in flight per cluster (<= warps per CTA, <= kMaxSeats)
   int32_t banks;         // 2: optimiser steps of one half of the seats overlap the sweeps of the other
   int32_t reserved;      // warps of the leader CTA that never sweep (0 or 2), see choose_geometry
+  // seat layout in doubles, computed once on the host (fit_seat_layout): the kernel would
+  // otherwise re-derive it from (kmax, K, warps, cluster size, ...) at every use
+  int32_t seat_d, off_cred, off_cst, off_imm, off_insn;
   int32_t kmax, max_insn, max_imm;  // maxima over this launch's programs (size the seat areas)
   int32_t n_cols;                   // columns of X this launch's programs read
   int32_t col_of_var[VSR_MAX_VARS]; // slice column of variable j (-1: unused)
@@ -359,6 +362,22 @@ __host__ __device__ inline size_t fit_seat_doubles(int kmax, int K, int nwarps, 
   (void)nwarps;
   return (d + 1) & ~(size_t)1;  // 16-byte multiple
 }
+// offsets (in doubles) of the parts of a seat, and the seat's size
+struct SeatLayout {
+  int seat_d, off_ws, off_cred, off_cst, off_imm, off_insn;
+};
+__host__ __device__ inline SeatLayout fit_seat_layout(int kmax, int K, int nwarps, int cs, int max_insn,
+                                                      int max_imm) {
+  SeatLayout L;
+  L.off_ws = kFitStateDoubles;
+  L.off_cred = L.off_ws + fit_workspace_doubles(kmax);
+  L.off_cst = L.off_cred + cs * (K + 1);
+  L.off_imm = L.off_cst + kSeatCstDoubles;
+  L.off_insn = L.off_imm + VSR_MAX_IMMS;
+  L.seat_d = (int)fit_seat_doubles(kmax, K, nwarps, cs, max_insn, max_imm);
+  return L;
+}
+
 __host__ __device__ inline size_t fit_smem_bytes(int seats, int kmax, int K, int nwarps, int cs,
                                                  int max_insn, int max_imm, int n_cols, int stride,
                                                  int elem) {
@@ -556,14 +575,14 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   const int warp = tid >> 5;
   const int G = a.seats;
 
-  const size_t seat_d = fit_seat_doubles(a.kmax, K, nw, cs, a.max_insn, a.max_imm);
-  const int wsd = fit_workspace_doubles(a.kmax);
+  const int seat_d = a.seat_d;
+  const int wsd = a.off_cred - kFitStateDoubles;
 #define VSR_SEAT_STATE(g) (smem + (size_t)(g)*seat_d)
 #define VSR_SEAT_WS(g) (VSR_SEAT_STATE(g) + kFitStateDoubles)
-#define VSR_SEAT_CRED(g) (VSR_SEAT_WS(g) + wsd)
-#define VSR_SEAT_CST(g) (reinterpret_cast<T*>(VSR_SEAT_CRED(g) + cs * (K + 1)))
-#define VSR_SEAT_IMM(g) (VSR_SEAT_CRED(g) + cs * (K + 1) + kSeatCstDoubles)
-#define VSR_SEAT_INSN(g) (reinterpret_cast<vsr_insn_t*>(VSR_SEAT_IMM(g) + VSR_MAX_IMMS))
+#define VSR_SEAT_CRED(g) (VSR_SEAT_STATE(g) + a.off_cred)
+#define VSR_SEAT_CST(g) (reinterpret_cast<T*>(VSR_SEAT_STATE(g) + a.off_cst))
+#define VSR_SEAT_IMM(g) (VSR_SEAT_STATE(g) + a.off_imm)
+#define VSR_SEAT_INSN(g) (reinterpret_cast<vsr_insn_t*>(VSR_SEAT_STATE(g) + a.off_insn))
 
   // ---- this CTA's slice of the points ----
   // CTAs 1..cs-1 take `per` points each, the leader (rank 0) takes what is left at the end: in
