@@ -71,6 +71,19 @@ struct Lanes {
     for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
     return v;
   }
+  // three sums with their butterflies interleaved: the same additions in the same order as
+  // three calls of sum(), one third of the latency (the optimiser warp is latency-bound)
+  static __device__ __forceinline__ void sum3(double& a, double& b, double& c) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      const double ta = __shfl_xor_sync(0xffffffffu, a, m);
+      const double tb = __shfl_xor_sync(0xffffffffu, b, m);
+      const double tc = __shfl_xor_sync(0xffffffffu, c, m);
+      a += ta;
+      b += tb;
+      c += tc;
+    }
+  }
   static __device__ __forceinline__ double maxv(double v) {
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) {
@@ -86,12 +99,18 @@ struct Lanes {
   static int step() { return 1; }
   static void sync() {}
   static double sum(double v) { return v; }
+  static void sum3(double&, double&, double&) {}
   static double maxv(double v) { return v; }
   static bool any(bool b) { return b; }
   static bool all(bool b) { return b; }
 #endif
 };
 // element i of a length-k vector is handled by lane i (all of them by the host's one lane)
+#if defined(__CUDA_ARCH__)
+#define VSR_UNROLL4 _Pragma("unroll 4")
+#else
+#define VSR_UNROLL4
+#endif
 #define VSR_FOR_K(i, k) for (int i = Lanes::first(); i < (k); i += Lanes::step())
 
 // DCSRCH task codes
@@ -534,6 +553,7 @@ VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
           double d = 0.0;
           VSR_FOR_K(i, k) {
             double acc = 0.0;
+            VSR_UNROLL4
             for (int j = 0; j < k; ++j) acc += S.H[i * k + j] * S.gfk[j];
             S.pk[i] = -acc;
             d += S.gfk[i] * -acc;
@@ -752,9 +772,8 @@ VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
             if (nan_d(S.gfk[i])) gnan = true;
             if (abs_d(S.gfk[i]) > gm) gm = abs_d(S.gfk[i]);
           }
-          pn2 = Lanes::sum(pn2);
-          xn2 = Lanes::sum(xn2);
-          const double rhok_inv = Lanes::sum(ys);
+          Lanes::sum3(pn2, xn2, ys);
+          const double rhok_inv = ys;
           gm = Lanes::maxv(gm);
           gnan = Lanes::any(gnan);
           S.it += 1;
@@ -777,17 +796,21 @@ VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
           Lanes::sync();     // yk, sk complete
           VSR_FOR_K(i, k) {
             double ui = 0.0;
+            VSR_UNROLL4
             for (int j = 0; j < k; ++j) ui += S.H[i * k + j] * yk[j];
+            VSR_UNROLL4
             for (int j = 0; j < k; ++j) S.H[i * k + j] -= rhok * ui * sk[j];
           }
           Lanes::sync();  // T complete
           VSR_FOR_K(j, k) {
             double a2 = 0.0;
+            VSR_UNROLL4
             for (int l = 0; l < k; ++l) a2 += yk[l] * S.H[l * k + j];
             w[j] = a2;
           }
           Lanes::sync();  // w complete
           VSR_FOR_K(i, k) {
+            VSR_UNROLL4
             for (int j = 0; j < k; ++j) S.H[i * k + j] += rhok * sk[i] * sk[j] - rhok * sk[i] * w[j];
           }
         }
