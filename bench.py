@@ -270,6 +270,10 @@ def main():
         res = eng.fit(rp, rs, x0d, opts)
         ev[i][1].record()
         results.append(res)
+        # a driver needs the result of one beam before it decodes the next; it also keeps the
+        # next step's launches out of the hardware queues while this one runs (enqueueing all
+        # steps back to back made every step ~10 % slower, tools/exp_valueloop.py)
+        torch.cuda.synchronize()
     barrier()
     t_wall1 = time.time()
     step_ms = [a.elapsed_time(b) for a, b in ev]

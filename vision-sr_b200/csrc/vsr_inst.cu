@@ -11,12 +11,33 @@ cudaError_t launch_fit_T(const FitArgs& a, int threads, int cs, size_t smem, int
   constexpr int P = points_per_thread(K);
   auto kern = fit_kernel<T, K, P>;
   if (threads > fit_max_threads<T, K>()) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)std::max<size_t>(smem, 1024));
+  // function attributes and the occupancy answer are cached per instantiation: they are driver
+  // calls, and vsr_fit launches up to eleven groups per call
+  struct Occ { int threads, cs; size_t smem; int resident; };
+  struct PerDevice {
+    size_t smem_limit = 0;
+    bool wide_clusters = false;
+    Occ occ[8];
+    int n_occ = 0;
+  };
+  static PerDevice cache[32];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (cs > 8) {
+  PerDevice& pd = cache[dev & 31];
+  size_t& smem_limit = pd.smem_limit;
+  bool& wide_clusters = pd.wide_clusters;
+  Occ* occ = pd.occ;
+  int& n_occ = pd.n_occ;
+  if (smem > smem_limit) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
+    if (e != cudaSuccess) return e;
+    smem_limit = smem;
+  }
+  if (cs > 8 && !wide_clusters) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return e;
+    wide_clusters = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)cs);
@@ -30,9 +51,16 @@ cudaError_t launch_fit_T(const FitArgs& a, int threads, int cs, size_t smem, int
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  int resident = 0;
-  e = cudaOccupancyMaxActiveClusters(&resident, kern, &cfg);
-  if (e != cudaSuccess) return e;
+  int resident = -1;
+  for (int i = 0; i < n_occ; ++i)
+    if (occ[i].threads == threads && occ[i].cs == cs && occ[i].smem == smem) resident = occ[i].resident;
+  if (resident < 0) {
+    e = cudaOccupancyMaxActiveClusters(&resident, kern, &cfg);
+    if (e != cudaSuccess) return e;
+    occ[n_occ % 8] = Occ{threads, cs, smem, resident};
+    ++n_occ;
+    if (n_occ > 8) n_occ = 8;  // keep overwriting slot 0.. when full
+  }
   if (resident < 1) return cudaErrorLaunchOutOfResources;
   cfg.gridDim = dim3((unsigned)(std::max(1, std::min(clusters, resident)) * cs));
   return cudaLaunchKernelEx(&cfg, kern, a);
