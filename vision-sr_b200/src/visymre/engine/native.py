@@ -9,6 +9,12 @@ import ctypes
 import os
 import subprocess
 
+# vsr_fit launches one kernel per tangent width on its own stream.  With CUDA's default of 8
+# hardware queues the streams of back-to-back fits alias and every fit runs ~10 % slower when
+# the next one is already enqueued (tools/exp_valueloop.py); 32 queues remove that.  Only
+# effective if set before the CUDA context exists, harmless otherwise.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from . import isa
 
 # VSR_LIB: A/B measurement hook (another build of the same ABI)
