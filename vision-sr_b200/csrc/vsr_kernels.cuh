@@ -1,10 +1,11 @@
 // vsr_kernels.cuh -- sm_100a kernels of the refinement engine.
 //
-//   fit_kernel<T,K,P>   one thread-block CLUSTER per (candidate, restart) run: thread 0 of the
-//                       leader CTA advances the BFGS state machine (vsr_bfgs.h); whenever it
-//                       asks for the objective all threads of all CTAs sweep their slice of
-//                       the points -- TMA-staged once into distributed shared memory --
-//                       through the interpreter (vsr_interp.h).  Replaces
+//   fit_kernel<T,K,P>   PERSISTENT thread-block clusters that keep several (candidate, restart)
+//                       runs in flight each ("seats"): reserved warps of the leader CTA advance
+//                       the BFGS state machines (vsr_bfgs.h) of one half of the seats while
+//                       every other warp of the cluster sweeps its slice of the points --
+//                       TMA-staged once into distributed shared memory -- through the
+//                       interpreter (vsr_interp.h) for the other half.  Replaces
 //                       minimize(safe_loss, x0, 'BFGS') + the lambdified loss
 //                       (reference bfgs.py:102-118).
 //   eval_kernel<T,K,P>  batched loss (+ gradient) of (program, constants) pairs; grid.y
@@ -12,9 +13,9 @@
 //   eval_finalize       deterministic fixed-order sum of the split partials.
 //
 // Work mapping: lanes stride over points (coalesced column reads), P points per thread
-// share one instruction decode; per-thread partial sums are fp64; reduction is
-// __shfl_xor_sync inside the warp, shared memory across the CTA, fixed order throughout
-// so results are reproducible run to run.
+// share one instruction decode; per-thread partial sums are fp64 and parked in shared memory,
+// one warp per component sums them (block_totals); fixed order throughout, so results are
+// reproducible run to run.
 #ifndef VSR_KERNELS_CUH_
 #define VSR_KERNELS_CUH_
 
@@ -328,15 +329,15 @@ __device__ __forceinline__ void sweep_slice(const vsr_insn_t* prog, const double
 // ---- fit kernel ------------------------------------------------------------------------------------
 // PERSISTENT thread-block clusters, each working on `seats` (candidate, restart) runs at a time.
 //
-// A pass of one run is: optimiser step (one warp, ~5-10 k cycles of dependent scalar work) ->
+// A pass of one run is: optimiser step (one warp, 16-21 k cycles of dependent scalar work) ->
 // sweep of all points through the interpreter (all warps of all CTAs) -> reduction.  With one run
-// per cluster every warp but one idles through the optimiser step and both cluster barriers
+// per cluster every warp but one idles through the optimiser step and the cluster barriers
 // (ncu: two thirds of all warp samples sat in barrier waits).  Here a cluster holds G runs in
-// "seats"; the G optimiser steps run CONCURRENTLY on warps 0..G-1 of the leader CTA, then all
-// warps sweep the G requests back to back, so the serial part is paid once per G sweeps.  A seat
-// whose run finishes takes the next run from the launch's queue (one atomic), so seats stay
-// full until the queue drains; the last long runs then have their cluster to themselves and
-// advance at single-run latency.
+// "seats", split in two banks: while the optimiser turns of one bank run on reserved warps of the
+// leader CTA, all other warps sweep the requests of the other bank back to back (the schedule is
+// described at the loop below).  A seat whose run finishes takes the next run from the launch's
+// queue (one atomic), so seats stay full until the queue drains; the last long runs then have
+// their cluster to themselves and advance at single-run latency.
 //
 // The points are split in contiguous slices, one per CTA.  When a slice fits, the columns the
 // launch's programs read and y are staged ONCE per cluster into shared memory by TMA bulk
@@ -711,7 +712,7 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
               w = (w & ~((vsr_insn_t)0xffff << 16)) | ((vsr_insn_t)a.col_of_var[VSR_IDX(w)] << 16);
             s_insn[i] = predecode(w);
           }
-          if (stid == 0) s_insn[ni] = 0;  // the pad word the interpreter prefetches
+          if (stid == 0) s_insn[ni] = 0;  // pad word after END
           for (int i = stid; i < nm; i += snt) s_imm[i] = a.pt.imms[m0 + i];
         }
       }
