@@ -222,3 +222,29 @@ def test_widest_dual_kernel_and_fd_fallback_on_monomial_bases(eng):
             np.testing.assert_allclose(c[r, :k], sol, rtol=2e-3, atol=2e-4)
         resid = y - A @ sol
         assert res.final_mse.cpu().numpy().min() == pytest.approx(np.mean(resid * resid), rel=1e-5)
+
+
+def test_fp32_sweeps_with_many_runs_in_flight(eng):
+    """fp32 point evaluation (config 4's proposal: fp32 sweeps, fp64 optimiser state) through the
+    seat machinery: 12 programs x 8 restarts in one launch reach the fp64 losses to fp32 accuracy,
+    and the launch is reproducible bit for bit."""
+    X, y, progs, run_prog, x0 = _mixed_runs(8)
+    X32, y32 = X.astype(np.float32), y.astype(np.float32)
+    eng.set_points(X32, y32, dtypes=(fitter.F32, fitter.F64), n_vars=3)
+    eng.set_programs(progs)
+    n = len(run_prog)
+    o32 = fitter.default_opts(eval_dtype=fitter.F32, score_dtype=fitter.F32)
+    o64 = fitter.default_opts(eval_dtype=fitter.F64, score_dtype=fitter.F64)
+    a = eng.fit(run_prog, np.arange(n), x0, o32)
+    b = eng.fit(run_prog, np.arange(n), x0, o32)
+    c = eng.fit(run_prog, np.arange(n), x0, o64)
+    la, lb, lc = (r.final_mse.cpu().numpy() for r in (a, b, c))
+    assert np.array_equal(la, lb, equal_nan=True)
+    ks = np.array([p.k for p in progs])[run_prog]
+    # best restart per program: fp32 sweeps find the fp64 optimum up to fp32 rounding of the loss
+    for j in range(len(progs)):
+        sel = run_prog == j
+        if ks[sel][0] == 0:
+            continue
+        best32, best64 = np.nanmin(la[sel]), np.nanmin(lc[sel])
+        assert best32 <= best64 * (1 + 1e-3) + 1e-6, (j, best32, best64)
