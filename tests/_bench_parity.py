@@ -1,11 +1,12 @@
-"""GPU probe (uses the oracle, so it is measurement / test infrastructure): parity statistic on
-the BENCH workload itself.  For every candidate of a few beams (R = 10, N = 10 000) compare the
+"""TEST INFRASTRUCTURE (imports the oracle): parity statistic on the BENCH workload itself.  For every candidate of a few beams (R = 10, N = 10 000) compare the
 best-of-R loss of the drop-in bfgs_batch (FD-gradient parity mode and the default dual mode)
 with the oracle's (scipy BFGS over numpy columns, the reference's algorithm) from the same
 starting points.  SURVEY 8c: same basin  <=>  |dloss| <= 1e-6*max(1,|loss|) + 1e-9."""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "vision-sr_b200"))
+for _p in (ROOT, os.path.join(ROOT, "vision-sr_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 import warnings; warnings.filterwarnings("ignore")
 import numpy as np, torch
 from concurrent.futures import ProcessPoolExecutor
@@ -32,16 +33,18 @@ def same(a, b):
     return abs(a - b) <= 1e-6 * max(1.0, abs(b)) + 1e-9
 
 
-if __name__ == "__main__":
-    nb = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+def statistic(nb=3, verbose=True):
     R = 10
     beams = bench.make_workload(nb, 10_000, 64, R)
     td = g.make_test_data()
     tot = {"fd": [0, 0], "dual": [0, 0]}
     mism = []
+    # the oracle first, in worker processes forked BEFORE this process touches CUDA
     with ProcessPoolExecutor(min(16, os.cpu_count() or 4)) as ex:
-        for b in beams:
-            ref = list(ex.map(_oracle, [(b.tokens[j], b.X, b.y, b.x0[j], R) for j in range(len(b.tokens))]))
+        refs = [list(ex.map(_oracle, [(b.tokens[j], b.X, b.y, b.x0[j], R) for j in range(len(b.tokens))]))
+                for b in beams]
+    if True:
+        for b, ref in zip(beams, refs):
             Xd = torch.from_numpy(b.X[None]).cuda(); yd = torch.from_numpy(b.y).cuda()
             line = {"beam": b.name}
             for mode in ("fd", "dual"):
@@ -56,10 +59,19 @@ if __name__ == "__main__":
                         mism.append((b.name, mode, got, r))
                 line[mode] = f"{ok}/{n}"
                 tot[mode][0] += ok; tot[mode][1] += n
-            print(json.dumps(line), flush=True)
-    print(json.dumps({"total": {m: f"{a}/{b} = {a / max(1, b):.3f}" for m, (a, b) in tot.items()}}))
+            if verbose:
+                print(json.dumps(line), flush=True)
+    if verbose:
+        print(json.dumps({"total": {m: f"{a}/{b} = {a / max(1, b):.3f}" for m, (a, b) in tot.items()}}))
     lower = sum(1 for _, _, a, r in mism if a is not None and r is not None and a < r)
     close = sum(1 for _, _, a, r in mism if a is not None and r is not None and abs(a - r) <= 1e-3 * max(1.0, abs(r)))
-    print(json.dumps({"mismatches": len(mism), "ours_lower": lower, "within_1e-3": close}))
-    for m in mism[:40]:
-        print("   ", m)
+    junk = sum(1 for _, _, a, r in mism if r is not None and r < 0)
+    if verbose:
+        print(json.dumps({"mismatches": len(mism), "ours_lower": lower, "within_1e-3": close, "oracle_negative": junk}))
+        for m in mism[:40]:
+            print("   ", m)
+    return {m: a / max(1, b) for m, (a, b) in tot.items()}, mism
+
+
+if __name__ == "__main__":
+    statistic(int(sys.argv[1]) if len(sys.argv) > 1 else 3)
