@@ -15,8 +15,10 @@ shipped vocabulary, synthetic points from the table's ranges, beam = 64 candidat
 `--impl reference` times the reference's CPU algorithm for this path (the oracle port:
 scipy BFGS over numpy columns, one process per host core as model.py:490 does) on a
 bounded sample of the same workload.
-N > 1 (torchrun): beams are independent units; rank r takes beams r, r+N, ... -- weak
-scaling, no data-path collective.
+N > 1 (torchrun): weak scaling = fixed work per GPU: the job is N times the `steps` beams of the
+one-GPU job; beams are independent units, every rank holds them resident and the ranks claim
+steps from one pool (own stripe first, then what the others have not started) -- no data-path
+collective.
 """
 import argparse
 import json
@@ -87,6 +89,59 @@ def make_workload(n_beams, n_points, n_cand, n_restarts, offset=0, stride=1):
     while len(beams) < n_beams:      # fewer usable rows than steps: cycle
         beams.append(beams[len(beams) % len(beams)])
     return beams[:n_beams]
+
+
+def make_shared_workload(n_distinct, n_points, n_cand, n_restarts, rank, world, dist):
+    """The same list of distinct beams on every rank: rank r generates rows r, r+world, ... with its
+    share of the host cores, one all_gather_object puts the lists together (row order)."""
+    from concurrent.futures import ProcessPoolExecutor
+    from src.visymre.workloads import generator as g
+    t = g.load_tables()
+    rows = [(e, r) for e, r in enumerate(t["feynman"]) if not r["name"].startswith("test_")]
+    rows = rows[: int(n_distinct * 1.3) + 4]
+    mine = rows[rank::world]
+    jobs = [(e, r, n_points, n_cand, n_restarts) for e, r in mine]
+    workers = max(1, min(32, (os.cpu_count() or 2) // world))
+    with ProcessPoolExecutor(workers) as ex:
+        got = list(ex.map(_gen_beam, jobs))
+    parts = [None] * world
+    dist.all_gather_object(parts, got)
+    beams = []
+    for i in range(len(rows)):          # back to row order
+        b = parts[i % world][i // world]
+        if b is not None:
+            beams.append(b)
+    if not beams:
+        raise RuntimeError("no beam could be generated")
+    return beams[:n_distinct] if len(beams) >= n_distinct else beams
+
+
+class Claims:
+    """Hands out the global step indices 0..n-1 of the job to the ranks of ONE node: rank r takes its
+    own stripe r, r+world, ... first and then what the others have not started yet (from the end of
+    their stripes).  A claim is an O_EXCL file creation in a directory all ranks see; with one
+    rank it is a plain counter.  Beams are independent units: this is scheduling, not a data-path
+    collective, and it keeps one rank with unlucky (long) beams from holding the job up."""
+
+    def __init__(self, n, rank, world, root, tag):
+        self.n, self.rank, self.world, self.root, self.tag = n, rank, world, root, tag
+        own = list(range(rank, n, world))
+        others = [i for i in range(n - 1, -1, -1) if i % world != rank]
+        self.order = own + others
+        self.pos = 0
+
+    def next(self):
+        while self.pos < len(self.order):
+            i = self.order[self.pos]
+            self.pos += 1
+            if self.world == 1:
+                return i
+            try:
+                os.close(os.open(os.path.join(self.root, f"{self.tag}_{i}"), os.O_CREAT | os.O_EXCL | os.O_WRONLY))
+                return i
+            except FileExistsError:
+                continue
+        return None
 
 
 # ---- clocks ---------------------------------------------------------------------------------
@@ -220,8 +275,26 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n_steps = args.warmup + args.steps
-    beams = make_workload(n_steps, args.points, args.cand, args.restarts, offset=rank, stride=world)
+    # The job is world x steps beams (weak scaling).  Every rank holds the distinct beams of the job
+    # resident and the ranks claim steps from one pool (class Claims): step i of the job is beam
+    # job[i].  With one rank this is the plain sequence warmup beams, then the timed beams.
+    n_job = world * args.steps
+    if world > 1:
+        beams = make_shared_workload(args.warmup + args.steps, args.points, args.cand, args.restarts, rank, world, dist)
+        claim_root = [None]
+        if rank == 0:
+            import tempfile
+            claim_root[0] = tempfile.mkdtemp(prefix="vsr_bench_")
+        dist.broadcast_object_list(claim_root, src=0)
+        claim_root = claim_root[0]
+    else:
+        beams = make_workload(args.warmup + args.steps, args.points, args.cand, args.restarts)
+        claim_root = None
+    D = len(beams)
+    # weak scaling = fixed work per GPU: the job at N GPUs is N times the `steps` beams of the
+    # one-GPU job (every repetition is a full, independent refinement)
+    job = [(args.warmup + (i % args.steps)) % D for i in range(n_job)]   # beam index of every timed step
+    warm = [s % D for s in range(args.warmup)]
     R, C = args.restarts, args.cand
     eval_dt = fitter.F32 if args.precision == "fp32" else fitter.F64
     opts = fitter.default_opts(grad_mode=isa.GRAD_MODE["VSR_GRAD_FD" if args.grad_mode == "fd" else "VSR_GRAD_DUAL"],
@@ -253,46 +326,53 @@ def main():
     import gc
     gc.collect()
     gc.disable()   # a generation-2 collection over sympy's object graph stalls the host for ~50-100 ms
-    for s in range(args.warmup):
-        eng, x0d, rp, rs, _ = setups[s]
+    for bi in warm:
+        eng, x0d, rp, rs, _ = setups[bi]
         eng.fit(rp, rs, x0d, opts)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     t_wall0 = time.time()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = sum(s[0].launches for s in setups)
-    results = []
-    for i in range(args.steps):
-        eng, x0d, rp, rs, _ = setups[args.warmup + i]
+    claims = Claims(n_job, rank, world, claim_root, "v")
+    prof = [0.0, 0.0, 0.0, 0.0]
+    mine, ev, results = [], [], []           # the steps this rank ran: beam index, events, result
+    while True:
+        i = claims.next()
+        if i is None:
+            break
+        bi = job[i]
+        eng, x0d, rp, rs, _ = setups[bi]
         eng.set_profiling(True)
         flush.fill_(i & 0xFF)          # evict the previous step's data from L2 (untimed)
-        ev[i][0].record()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
         res = eng.fit(rp, rs, x0d, opts)
-        ev[i][1].record()
-        results.append(res)
+        b_.record()
         # a driver needs the result of one beam before it decodes the next; it also keeps the
         # next step's launches out of the hardware queues while this one runs (enqueueing all
         # steps back to back made every step ~10 % slower, tools/exp_valueloop.py)
         torch.cuda.synchronize()
+        mine.append(bi)
+        ev.append((a, b_))
+        results.append(res)
+        p = eng.read_profile()         # per step: an engine can serve several steps of the job
+        eng.set_profiling(False)
+        prof = [x + y for x, y in zip(prof, p)]
     barrier()
     t_wall1 = time.time()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
+    step_ms = [a.elapsed_time(b_) for a, b_ in ev]
     total_ms = float(sum(step_ms))
-    if rank == 0:
-        print("step_ms " + " ".join(f"{b.name}:{m:.1f}" for b, m in zip(beams[args.warmup:], step_ms)), file=sys.stderr)
+    print(f"rank {rank}: {len(mine)} steps, {total_ms:.1f} ms: " + " ".join(f"{beams[bi].name}:{m:.1f}" for bi, m in zip(mine, step_ms)),
+          file=sys.stderr)
     launches = sum(s[0].launches for s in setups) - launches0
-    fit_ms = fit_n = score_ms = 0.0
-    for i in range(args.steps):
-        p = setups[args.warmup + i][0].read_profile()
-        fit_ms, fit_n, score_ms = fit_ms + p[0], fit_n + p[1], score_ms + p[2]
-        setups[args.warmup + i][0].set_profiling(False)
+    fit_ms, fit_n, score_ms = prof[0], prof[1], prof[2]
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 
     # ---- algorithmic work of the timed steps (from the runs' own evaluation counts) ----
     flops = pevals = abytes = 0.0
     es = 4 if args.precision == "fp32" else 8
-    for i in range(args.steps):
-        b = beams[args.warmup + i]
+    for i, bi in enumerate(mine):
+        b = beams[bi]
         info = results[i].info.cpu().numpy().reshape(C, R, 4)
         N = b.X.shape[0]
         for j, p in enumerate(b.programs):
@@ -308,11 +388,21 @@ def main():
     # device buffers are allocated by the first (untimed) steps and reused afterwards
     e2e_ms, h2d, d2h = 0.0, 0, 0
     e2e_eng = fitter.Engine(dev)
-    for i in range(-min(2, args.warmup), args.steps):
-        n_vars_i = setups[args.warmup + i][0].n_vars
-        _, _, rp, rs, x0h = setups[args.warmup + i]
+    e2e_claims = Claims(n_job, rank, world, claim_root, "e")
+    e2e_warm = list(warm[-min(2, len(warm)):])
+    barrier()
+    while True:
+        if e2e_warm:
+            bi, timed = e2e_warm.pop(0), False
+        else:
+            i = e2e_claims.next()
+            if i is None:
+                break
+            bi, timed = job[i], True
+        n_vars_i = setups[bi][0].n_vars
+        _, _, rp, rs, x0h = setups[bi]
         eng = e2e_eng
-        b = beams[args.warmup + i]
+        b = beams[bi]
         Xc = np.ascontiguousarray(b.X[:, :n_vars_i].T)  # column-major host copy (layout prepared once)
         yh = np.ascontiguousarray(b.y)
         insn_off = np.zeros(C + 1, dtype=np.int32)
@@ -338,7 +428,7 @@ def main():
                                   warps_per_run=args.warps)
         out = eng.fit_host(rp, rs, x0h, o64)
         dt = (time.perf_counter() - t0) * 1e3
-        if i >= 0:
+        if timed:
             e2e_ms += dt
             if rank == 0:
                 print(f"e2e_ms {b.name}:{dt:.1f} (points {1e3 * (t1 - t0):.1f} programs {1e3 * (t2 - t1):.1f})", file=sys.stderr)
@@ -355,7 +445,7 @@ def main():
         td = g.make_test_data()
         cfg = g.make_cfg(R, C, grad_mode=args.grad_mode)
         for i in range(min(args.steps, 4)):
-            b = beams[args.warmup + i]
+            b = beams[job[i]]
             Xd = torch.from_numpy(b.X[None]).to(dev)
             yd = torch.from_numpy(b.y).reshape(1, -1, 1).to(dev)
             hyps = [(-float(j), t) for j, t in enumerate(b.tokens)]
@@ -433,9 +523,13 @@ def main():
                         "is FP-pipe bound, not HBM bound: see profiles/ for ncu pipe utilisation"},
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(beams[args.warmup:], R, args.cpu_sample)
+            line["cpu_baseline"] = cpu_baseline([beams[bi] for bi in job], R, args.cpu_sample)
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
+        if rank == 0:
+            import shutil
+            shutil.rmtree(claim_root, ignore_errors=True)
         dist.destroy_process_group()
 
 

@@ -403,7 +403,7 @@ int vsr_create(int device, vsr_handle** out) {
   if (e == cudaSuccess) e = h->d_lists.reserve(256 << 10);
   if (e == cudaSuccess) e = h->d_queue.reserve(64 * sizeof(int32_t));
   if (e == cudaSuccess) e = h->d_partial.reserve(1 << 20);
-  for (int i = 0; i < 12 && e == cudaSuccess; ++i) {
+  for (int i = 0; i < 8 && e == cudaSuccess; ++i) {
     cudaStream_t s2;
     e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
     if (e != cudaSuccess) break;
