@@ -169,6 +169,11 @@ int vsr_set_profiling(vsr_handle* h, int32_t on);
  * barriers, sweep, reductions) and the number of passes.  NULL switches it off. */
 int vsr_set_phase_buffer(vsr_handle* h, void* dev_i64_nslots_by_8);
 int vsr_read_profile(vsr_handle* h, double out[4]);
+/* Measurement hook: overrides the launch geometry of vsr_fit -- cluster size, threads per CTA, runs
+ * in flight per cluster ("seats") and optimiser warps of the leader CTA (< 0: none); 0 keeps the
+ * built-in choice of that item.  The environment variable VSR_GEOMETRY="cluster:threads:seats:opt"
+ * is read ONCE, by vsr_create, as the initial value. */
+int vsr_set_geometry(vsr_handle* h, int32_t cluster, int32_t threads, int32_t seats, int32_t opt_warps);
 
 #ifdef __cplusplus
 }

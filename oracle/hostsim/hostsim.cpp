@@ -162,9 +162,9 @@ int hostsim_fit(const vsr_insn_t* raw_prog, const double* imm, int k, const void
     double s = 0.0, g[VSR_MAX_DUAL] = {0};
     int rc;
     if (dtype == VSR_F64)
-      rc = sweep_dispatch<double>(K, prog, imm, S.xe, k, (const double*)X, (const double*)y, N, &s, g);
+      rc = sweep_dispatch<double>(K, prog, imm, S.xe(), k, (const double*)X, (const double*)y, N, &s, g);
     else
-      rc = sweep_dispatch<float>(K, prog, imm, S.xe, k, (const float*)X, (const float*)y, N, &s, g);
+      rc = sweep_dispatch<float>(K, prog, imm, S.xe(), k, (const float*)X, (const float*)y, N, &s, g);
     if (rc) return rc;
     double f = O.loss_scale * (s / (double)N);
     if (!std::isfinite(f)) {
@@ -178,11 +178,11 @@ int hostsim_fit(const vsr_insn_t* raw_prog, const double* imm, int k, const void
     }
     S.rf = f;
     if (grad_mode == VSR_GRAD_DUAL)
-      for (int i = 0; i < k; ++i) S.rg[i] = g[i];
+      for (int i = 0; i < k; ++i) S.rg()[i] = g[i];
   }
   for (int i = 0; i < k; ++i) {
-    out_x[i] = S.xk[i];
-    out_lastx[i] = S.lastx[i];
+    out_x[i] = S.xk()[i];
+    out_lastx[i] = S.lastx()[i];
   }
   *out_fun = S.old_fval;
   *out_status = S.status;

@@ -279,3 +279,48 @@ def test_duplicate_skeletons_are_fitted_once_when_asked(golden, test_data):
     # all variants of the affine skeleton reach the exact fit either way
     for c in coll[:3]:
         assert float(c[2]) < 1e-12
+
+
+def _tok(test_data, words):
+    w2i = test_data.word2id
+    return [w2i["S"]] + [w2i[w] for w in words.split()] + [w2i["F"]]
+
+
+def test_all_pruned_singular_skeleton_keeps_the_unpruned_fit_and_the_beam(test_data):
+    """`c0 + x_1/c1` with both constants below the prune threshold substitutes to
+    zoo*x_1; the reference scores that prune 1e9 (bfgs.py:196-202) and keeps the fit.  One such
+    candidate must not fail the other candidates of the batch."""
+    rng = np.random.RandomState(3)
+    X = np.zeros((1, 200, 10))
+    X[0, :, 0] = rng.uniform(1, 2, 200)
+    y = np.zeros(200)                           # exact fit needs c0 = 0 and a huge c1
+    toks = [_tok(test_data, "add c div x_1 c"), _tok(test_data, "add c mul c x_1")]
+    # restart starts at (1e-4, 1e-4): loss is finite there, gradient pushes c1 up ... start INSIDE the
+    # prune band and cap the iterations by giving the exact zero-gradient point for the line
+    cfg = make_cfg(1, grad_mode="fd", prune_threshold=1e9)   # everything counts as "small"
+    outs = vbfgs.bfgs_batch(toks, torch.tensor(X, device="cuda:0"), torch.tensor(y, device="cuda:0"), cfg,
+                            test_data, x0=[np.array([[0.5, 3.0]]), np.array([[0.5, 0.25]])])
+    assert not any(isinstance(o, Exception) for o in outs), outs
+    ref = [vectorised.bfgs(t, X, y, cfg, test_data, x0=s) for t, s in
+           zip(toks, [np.array([[0.5, 3.0]]), np.array([[0.5, 0.25]])])]
+    for o, r in zip(outs, ref):
+        assert _same(float(o[2]), float(r[2])), (o, r)
+
+
+def test_nmse_scale_uses_the_full_y_when_rows_are_removed(test_data):
+    """with idx_remove the objective is divided by the mean of the FULL y
+    (bfgs.py:85-90); every final score is 1e9 then (shape mismatch), restart 0 is picked and its
+    last evaluated point depends on the objective's scale."""
+    rng = np.random.RandomState(4)
+    X = np.zeros((1, 60, 10))
+    X[0, :, 0] = rng.uniform(-2, 2, 60)
+    X[0, :7, 0] = 500.0                          # rows idx_remove drops
+    y = 3.0 + 2.0 * X[0, :, 0]
+    tok = _tok(test_data, "add c mul c x_1")
+    cfg = make_cfg(2, norm="NMSE", idx_remove=True, grad_mode="fd")
+    x0 = np.array([[1.0, 1.0], [-2.0, 0.5]])
+    got = vbfgs.bfgs(tok, torch.tensor(X, device="cuda:0"), torch.tensor(y, device="cuda:0"), cfg, test_data, x0=x0)
+    ref = vectorised.bfgs(tok, X, y, cfg, test_data, x0=x0)
+    assert float(got[2]) == float(ref[2]) == 1e9
+    # both stop where |grad|_inf <= gtol: the constants agree to the width of that valley floor
+    np.testing.assert_allclose(np.asarray(got[1], dtype=float), np.asarray(ref[1], dtype=float), rtol=1e-3, atol=1e-5)

@@ -24,21 +24,14 @@ def eng():
     return fitter.Engine("cuda:0")
 
 
-def _geometry(value):
-    """Context manager for the VSR_GEOMETRY measurement hook ("cluster:threads:seats")."""
+def _geometry(eng, value):
+    """Context manager for the launch-geometry measurement hook ("cluster:threads:seats")."""
     class _G:
         def __enter__(self):
-            self.old = os.environ.get("VSR_GEOMETRY")
-            if value:
-                os.environ["VSR_GEOMETRY"] = value
-            else:
-                os.environ.pop("VSR_GEOMETRY", None)
+            eng.set_geometry(value)
 
         def __exit__(self, *a):
-            if self.old is None:
-                os.environ.pop("VSR_GEOMETRY", None)
-            else:
-                os.environ["VSR_GEOMETRY"] = self.old
+            eng.set_geometry(None)
     return _G()
 
 
@@ -153,12 +146,12 @@ def test_results_do_not_depend_on_seats_or_queue_order(eng):
     or six per cluster, the queue shuffled or not, give bit-identical constants, losses and
     evaluation counts.  (The reference's runs are independent processes, model.py:490.)"""
     X, y, progs, run_prog, x0 = _mixed_runs(5)
-    with _geometry(""):
+    with _geometry(eng, ""):
         base = _fit_all(eng, X, y, progs, run_prog, x0)
     perm = np.random.RandomState(9).permutation(len(run_prog))
     variants = []
     for geo, order in (("8:640:1", None), ("8:640:6", None), ("", perm), ("8:640:2", perm[::-1])):
-        with _geometry(geo):
+        with _geometry(eng, geo):
             variants.append(_fit_all(eng, X, y, progs, run_prog, x0, order))
     for v in variants:
         for a, b in zip(base, v):

@@ -108,3 +108,45 @@ def test_allgather_world_size_2_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+WORKER_MORE_RANKS = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {pkg!r})
+    import numpy as np, torch, torch.distributed as dist
+    from src.visymre.engine import sharding
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+
+    class TableEngine:                    # stands in for the GPU fit: rows of a fixed table
+        device = torch.device("cpu")
+        calls = 0
+        def fit(self, run_prog, run_slot, x0, opts):
+            assert len(run_slot) > 0      # vsr_fit rejects an empty run list (VSR_EINVAL)
+            TableEngine.calls += 1
+            res = sharding.empty_result(1, 2, self.device)
+            for s in run_slot:
+                res.final_mse[s] = 0.25; res.loss[s] = 0.5; res.lastx[s] = torch.tensor([1.0, 2.0], dtype=torch.float64)
+            return res
+
+    # one candidate, one restart, two ranks: rank 1 holds no run and must still reach the all-gather
+    win, _ = sharding.fit_sharded(TableEngine(), [2], 1, np.zeros((1, 2)), None)
+    assert TableEngine.calls == (1 if rank == 0 else 0)
+    assert win[0, 0].item() == 0.25 and win[0, 1].item() == 0 and win[0, 3:5].tolist() == [1.0, 2.0], win
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+""")
+
+
+def test_more_ranks_than_runs_does_not_hang_gloo(tmp_path):
+    script = tmp_path / "worker2.py"
+    script.write_text(WORKER_MORE_RANKS.format(pkg=PKG))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         capture_output=True, text=True, env=env, timeout=120, cwd=ROOT)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2

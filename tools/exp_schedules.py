@@ -21,8 +21,7 @@ for b in beams:
     setups.append((eng, torch.from_numpy(x0).to(dev), np.repeat(np.arange(C), R), np.arange(C * R)))
 ref = None
 for sc in scheds:
-    if sc: os.environ["VSR_GEOMETRY"] = sc
-    else: os.environ.pop("VSR_GEOMETRY", None)
+    for su in setups: su[0].set_geometry(sc or None)
     ms = []
     losses = []
     nfev = 0

@@ -104,6 +104,7 @@ struct vsr_handle {
   DevBuf d_queue;    // one run counter per launch group (persistent clusters pull runs from it)
   PinnedBuf h_lists;
   int64_t launches = 0;
+  int hook[4] = {0, 0, 0, 0};  // VSR_GEOMETRY measurement hook, read once in vsr_create
   // measurement hooks
   bool profiling = false;
   long long* phase_cycles = nullptr;  // optional device buffer [n_slots][8], see vsr_set_phase_buffer
@@ -214,7 +215,7 @@ int next_pow2(int64_t v) {
 // long run is passes x latency per pass), and the slice fits the CTA's shared memory so the
 // points are read from HBM once per cluster.
 struct Geometry {
-  int cs, threads, stride, resident, seats, banks, reserved;
+  int cs, threads, stride, resident, seats, reserved;
   size_t smem;
 };
 
@@ -222,8 +223,10 @@ constexpr int kMaxCluster = 16;             // 16 needs the non-portable cluster
 constexpr int kDefaultSeats = 4;            // runs in flight per cluster
 constexpr size_t kSmemBudget = (VSR_FIT_MINCTAS == 1 ? 200 : 100) * 1024;  // per CTA, so that all co-resident CTAs keep their slices
 
+// want_reserved: optimiser warps of the leader CTA that never sweep; 0 = default (a function of
+// the CTA width), < 0 = none
 Geometry choose_geometry(int64_t N, int P, int cap_threads, int forced_warps, int kmax, int K, int max_insn,
-                         int max_imm, int n_cols, int elem, int max_cluster, int seats, int want_banks) {
+                         int n_cols, int elem, int max_cluster, int seats, int want_reserved) {
   Geometry g;
   const int64_t per_iter = (int64_t)cap_threads * P;
   int cs = 1;
@@ -233,39 +236,43 @@ Geometry choose_geometry(int64_t N, int P, int cap_threads, int forced_warps, in
   int threads = (int)std::min<int64_t>(cap_threads, ((per + P - 1) / P + 31) & ~(int64_t)31);
   if (forced_warps > 0) threads = std::min(cap_threads, 32 * forced_warps);
   threads = std::max(32, threads);
-  const int nw = threads / 32;
+  int nw = threads / 32;
   g.cs = cs;
-  g.threads = threads;
-  g.seats = std::max(1, std::min(std::min(seats, nw), (int)vsr::kMaxSeats));
-  // Slices: CTAs 1..cs-1 take `per` points, the leader the remainder.  When the cluster is big
-  // enough (cs >= 4, more than four warps) the remainder is sized for a leader that sweeps with
-  // two warps fewer: warps 0..1 of the leader are reserved for optimiser turns (in the two-bank
-  // schedule they run the optimisers of one half of the seats while everybody else sweeps the
-  // other half).  The layout and the set of sweeping warps are functions of (N, cs, threads)
-  // only, so a run's result does not depend on the number of seats or banks.
-  constexpr int kLeaderBusyWarps = 2;
-  g.banks = 1;
+  g.seats = std::max(1, std::min(seats, (int)vsr::kMaxSeats));
+  // Optimiser warps.  A CTA wide enough gives the last `res` warps of the cluster's leader to the
+  // optimiser turns for good (one per seat at the default width): they never sweep, so a turn never
+  // holds a sweep up.  The leader's slice is sized for its remaining warps: CTAs 1..cs-1 take
+  // `per` points, the leader the remainder.  The layout and the set of sweeping warps are functions
+  // of (N, cluster size, CTA width) only, so a run's result does not depend on the number of seats,
+  // on the queue order or on the other runs of the launch.
   g.reserved = 0;
-  if (cs >= 4 && nw > 2 * kLeaderBusyWarps && forced_warps <= 0) {
-    const int64_t denom = (int64_t)(cs - 1) * nw + (nw - kLeaderBusyWarps);
+  int res = want_reserved > 0 ? want_reserved : (want_reserved < 0 ? 0 : (nw >= 16 ? 4 : (nw >= 6 ? 2 : 0)));
+  if (forced_warps > 0) res = 0;
+  if (res > 0 && cs == 1 && threads + 32 * res <= cap_threads) {
+    // a single CTA: the optimiser warps come on top of the warps the points need
+    threads += 32 * res;
+    nw = threads / 32;
+    g.reserved = res;
+  } else if (res > 0 && nw > res) {
+    const int64_t denom = (int64_t)(cs - 1) * nw + (nw - res);
     int64_t per2 = (N * nw + denom - 1) / denom;
     per2 = (per2 + 31) & ~(int64_t)31;
     const int64_t lead = N - (int64_t)(cs - 1) * per2;
     // accept only if nobody needs more tile iterations than with equal slices
-    const int64_t tile = (int64_t)threads * P, tile_lead = (int64_t)(nw - kLeaderBusyWarps) * 32 * P;
+    const int64_t tile = (int64_t)threads * P, tile_lead = (int64_t)(nw - res) * 32 * P;
     const int64_t it0 = (per + tile - 1) / tile;
     const int64_t it_others = (per2 + tile - 1) / tile;
     const int64_t it_lead = lead > 0 ? (lead + tile_lead - 1) / tile_lead : 0;
-    if (it_others <= it0 && it_lead <= it0 && lead <= per2) {
+    if (it_others <= it0 && it_lead <= it0 && lead <= per2 && (cs == 1 || lead >= 0)) {
       per = per2;
-      g.reserved = kLeaderBusyWarps;  // warps 0..1 of the leader run optimiser turns, never sweep
-      if (want_banks >= 2 && g.seats >= 2) g.banks = 2;
+      g.reserved = res;
     }
   }
+  g.threads = threads;
   g.stride = (int)per;
-  const size_t with = vsr::fit_smem_bytes(g.seats, kmax, K, nw, cs, max_insn, max_imm, n_cols, (int)per, elem);
+  const size_t with = vsr::fit_smem_bytes(g.seats, kmax, K, nw, cs, max_insn, n_cols, (int)per, elem);
   g.resident = with <= kSmemBudget && per < (1 << 30);
-  g.smem = g.resident ? with : vsr::fit_smem_bytes(g.seats, kmax, K, nw, cs, max_insn, max_imm, -1, 0, elem);
+  g.smem = g.resident ? with : vsr::fit_smem_bytes(g.seats, kmax, K, nw, cs, max_insn, -1, 0, elem);
   return g;
 }
 
@@ -317,7 +324,6 @@ int run_eval_group(vsr_handle* h, int K, int dtype, const int32_t* d_prog, const
   a.partial = (double*)h->d_partial.p;
   a.nsplit = nsplit;
   a.nan_to_num = nan_to_num;
-  const int nw = threads / 32;
   const size_t smem = sizeof(double) * (size_t)((K + 1) * threads + kmax + 2 + max_imm + max_insn + 1);  // + pad word
   cudaError_t e = dtype == VSR_F64 ? launch_eval<double>(K, a, threads, smem, st)
                                    : launch_eval<float>(K, a, threads, smem, st);
@@ -328,6 +334,14 @@ int run_eval_group(vsr_handle* h, int K, int dtype, const int32_t* d_prog, const
       out_grad);
   VSR_CUDA(h, cudaGetLastError());
   h->launches += 2;
+  return VSR_OK;
+}
+
+// a program that reads x_j with j >= the uploaded n_vars would read past the last column
+int check_vars(vsr_handle* h, int prog, int dtype) {
+  const int nv = h->pts[dtype].n_vars;
+  if (nv < VSR_MAX_VARS && (h->h_varmask[prog] >> nv) != 0u)
+    return fail(h, VSR_EINVAL, "program %d reads a variable beyond the %d uploaded columns (dtype %d)", prog, nv, dtype);
   return VSR_OK;
 }
 
@@ -397,6 +411,7 @@ int vsr_create(int device, vsr_handle** out) {
   if (!h) return fail(nullptr, VSR_ENOMEM, "out of host memory");
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
+  if (const char* env = getenv("VSR_GEOMETRY")) sscanf(env, "%d:%d:%d:%d", &h->hook[0], &h->hook[1], &h->hook[2], &h->hook[3]);
   // scratch every fit needs, allocated here rather than inside the first fit: run lists (pinned
   // + device), run counters, eval partials, the side streams and their events
   e = h->h_lists.reserve(256 << 10);
@@ -457,6 +472,15 @@ int64_t vsr_launch_count(const vsr_handle* h) { return h ? h->launches : 0; }
 int vsr_set_phase_buffer(vsr_handle* h, void* dev_i64_nslots_by_8) {
   if (!h) return VSR_EINVAL;
   h->phase_cycles = (long long*)dev_i64_nslots_by_8;
+  return VSR_OK;
+}
+
+int vsr_set_geometry(vsr_handle* h, int32_t cluster, int32_t threads, int32_t seats, int32_t opt_warps) {
+  if (!h) return VSR_EINVAL;
+  h->hook[0] = cluster;
+  h->hook[1] = threads;
+  h->hook[2] = seats;
+  h->hook[3] = opt_warps;
   return VSR_OK;
 }
 
@@ -611,6 +635,7 @@ int vsr_eval(vsr_handle* h, const int32_t* prog_idx, const int32_t* const_row, i
     if (c < 0 || c >= h->n_programs) return fail(h, VSR_EINVAL, "pair %d: program %d out of range", p, c);
     const int k = h->h_k[c];
     if (k > kstride) return fail(h, VSR_EINVAL, "pair %d: %d constants > kstride %d", p, k, kstride);
+    if ((rc = check_vars(h, c, dtype))) return rc;
     int gi = 0;
     if (out_grad) {
       const int w = pick_width(k);
@@ -695,6 +720,7 @@ int vsr_score(vsr_handle* h, const int32_t* prog_idx, const int32_t* const_row, 
     const int c = prog_idx[p];
     if (c < 0 || c >= h->n_programs) return fail(h, VSR_EINVAL, "pair %d: program %d out of range", p, c);
     if (h->h_k[c] > kstride) return fail(h, VSR_EINVAL, "pair %d: %d constants > kstride %d", p, h->h_k[c], kstride);
+    if ((rc = check_vars(h, c, dtype))) return rc;
     kmax = std::max(kmax, h->h_k[c]);
     max_insn = std::max(max_insn, h->h_ninsn[c]);
     max_imm = std::max(max_imm, h->h_nimm[c]);
@@ -741,6 +767,8 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     if (c < 0 || c >= h->n_programs) return fail(h, VSR_EINVAL, "run %d: program %d out of range", r, c);
     const int k = h->h_k[c];
     if (k > kstride) return fail(h, VSR_EINVAL, "run %d: %d constants > kstride %d", r, k, kstride);
+    if (run_slot[r] < 0) return fail(h, VSR_EINVAL, "run %d: slot %d", r, run_slot[r]);
+    if ((rc = check_vars(h, c, opts->eval_dtype)) || (rc = check_vars(h, c, opts->score_dtype))) return rc;
     int mode = opts->grad_mode, K = 0;
     if (k > 0 && mode == VSR_GRAD_DUAL) {
       K = pick_width(k);
@@ -813,10 +841,8 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
   // one run counter per group: the persistent clusters of a launch pull their runs from it
   VSR_CUDA(h, h->d_queue.reserve(groups.size() * sizeof(int32_t)));
   VSR_CUDA(h, cudaMemsetAsync(h->d_queue.p, 0, groups.size() * sizeof(int32_t), st));
-  // measurement hook: VSR_GEOMETRY="cluster:threads:seats[:banks]" overrides the launch geometry
-  int hook_cluster = 0, hook_threads = 0, hook_seats = 0, hook_banks = 0;
-  if (const char* env = getenv("VSR_GEOMETRY"))
-    sscanf(env, "%d:%d:%d:%d", &hook_cluster, &hook_threads, &hook_seats, &hook_banks);
+  // measurement hook: VSR_GEOMETRY="cluster:threads:seats[:optimiser warps]" overrides the launch geometry
+  const int hook_cluster = h->hook[0], hook_threads = h->hook[1], hook_seats = h->hook[2], hook_reserved = h->hook[3];
 
   // groups run concurrently: group 0 on the caller's stream, the others on side streams
   // forked from / joined to it with events
@@ -865,25 +891,23 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     int n_cols = 0;
     for (int j = 0; j < VSR_MAX_VARS; ++j) a.col_of_var[j] = ((g.var_mask >> j) & 1u) ? n_cols++ : -1;
     Geometry geo = choose_geometry(g.kmax == 0 ? 1 : ps.n, P, cap, opts->warps_per_run, g.kmax, g.K, g.max_insn,
-                                   g.max_imm, n_cols, elem, max_cluster, hook_seats > 0 ? hook_seats : kDefaultSeats,
-                                   hook_banks > 0 ? hook_banks : 2);
+                                   n_cols, elem, max_cluster, hook_seats > 0 ? hook_seats : kDefaultSeats,
+                                   hook_reserved);
     if (g.kmax == 0) {  // runs without constants are only marked "not run": no points needed
       geo.resident = 0;
-      geo.smem = vsr::fit_smem_bytes(geo.seats, g.kmax, g.K, geo.threads / 32, geo.cs, g.max_insn, g.max_imm, -1, 0, elem);
+      geo.smem = vsr::fit_smem_bytes(geo.seats, g.kmax, g.K, geo.threads / 32, geo.cs, g.max_insn, -1, 0, elem);
     }
     a.phase_cycles = h->phase_cycles;
     a.resident = geo.resident;
     a.tma_ok = tma_ok ? 1 : 0;
     a.slice_stride = geo.stride;
     a.seats = geo.seats;
-    a.banks = geo.banks;
     a.reserved = geo.reserved;
     {
-      const vsr::SeatLayout L = vsr::fit_seat_layout(g.kmax, g.K, geo.threads / 32, geo.cs, g.max_insn, g.max_imm);
+      const vsr::SeatLayout L = vsr::fit_seat_layout(g.kmax, g.K, geo.cs, g.max_insn);
       a.seat_d = L.seat_d;
       a.off_cred = L.off_cred;
-      a.off_cst = L.off_cst;
-      a.off_imm = L.off_imm;
+      a.off_ctrl = L.off_ctrl;
       a.off_insn = L.off_insn;
     }
     a.kmax = g.kmax;
@@ -925,6 +949,10 @@ int vsr_fit_host(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot
   if (n_slots <= 0 || kstride < 1 || !x0 || !out_consts || !out_lastx || !out_loss ||
       !out_final_mse || !out_info)
     return fail(h, VSR_EINVAL, "bad fit_host arguments");
+  if (!run_slot || n_runs <= 0) return fail(h, VSR_EINVAL, "bad fit_host arguments");
+  for (int r = 0; r < n_runs; ++r)  // the kernels write rows run_slot[r] of buffers sized n_slots
+    if (run_slot[r] < 0 || run_slot[r] >= n_slots)
+      return fail(h, VSR_EINVAL, "run %d: slot %d outside [0, %d)", r, run_slot[r], n_slots);
   cudaStream_t st = (cudaStream_t)stream;
   VSR_CUDA(h, cudaSetDevice(h->device));
   const size_t row = (size_t)kstride * sizeof(double);

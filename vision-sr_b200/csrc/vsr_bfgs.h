@@ -23,11 +23,15 @@
 //
 // Execution model of fit_step on the device (a single GPU thread is ~30x slower than a
 // CPU core on serial code, so the linear algebra must not be serial): all 32 lanes of the
-// warp run the SAME control flow on identical scalar values -- each lane owns a private
-// FitState -- while the length-k vectors live in shared memory with element i handled by
-// lane i: O(k) loops take one step, O(k^2) ones (H g, the BFGS update) k steps, dot
-// products are warp-shuffle sums.  On the host `Lanes` degenerates to one lane and the
-// loops are ordinary loops.
+// warp run the SAME control flow on identical scalar values.  The scalar state (FitState)
+// lives in shared memory BETWEEN turns, one copy per run; a turn copies it into registers
+// at entry (fit_step works on a private copy, so no lane ever does a read-modify-write on
+// shared scalars and the compiler keeps them in registers across the vector stores) and
+// writes it back when it yields.  The length-k vectors live in shared memory with element i
+// handled by lane i % W (W = 8, 16 or 32 >= k: lanes beyond W repeat the work of the first W,
+// so every reduction is a log2(W)-step butterfly that leaves the same value in all lanes):
+// O(k) loops take one step, O(k^2) ones (H g, the BFGS update) k steps.  On the host `Lanes`
+// degenerates to one lane and the loops are ordinary loops.
 //
 // The same header is compiled by g++ into oracle/hostsim (CPU tests check the logic
 // against scipy itself); the product path only runs the CUDA build.
@@ -60,22 +64,25 @@ struct FitOpts {
 
 enum { VSR_NEED_EVAL = 1, VSR_DONE = 0 };
 
-// lane context of fit_step / fit_init
-struct Lanes {
+// lane context of fit_step / fit_init.  W: lanes that own vector elements (k <= W)
+template <int W>
+struct LanesT {
 #if defined(__CUDA_ARCH__)
-  static __device__ __forceinline__ int first() { return (int)(threadIdx.x & 31u); }
-  static __device__ __forceinline__ int step() { return 32; }
+  static __device__ __forceinline__ int first() { return (int)(threadIdx.x & (unsigned)(W - 1)); }
+  static __device__ __forceinline__ int step() { return W; }
   static __device__ __forceinline__ void sync() { __syncwarp(); }
+  // butterflies over the W lanes of a group: elements >= k are exact zeros, so the levels a
+  // 32-lane butterfly would add on top contribute x + 0 = x: same value, fewer shuffles
   static __device__ __forceinline__ double sum(double v) {
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    for (int m = W / 2; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
     return v;
   }
   // three sums with their butterflies interleaved: the same additions in the same order as
   // three calls of sum(), one third of the latency (the optimiser warp is latency-bound)
   static __device__ __forceinline__ void sum3(double& a, double& b, double& c) {
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
+    for (int m = W / 2; m > 0; m >>= 1) {
       const double ta = __shfl_xor_sync(0xffffffffu, a, m);
       const double tb = __shfl_xor_sync(0xffffffffu, b, m);
       const double tc = __shfl_xor_sync(0xffffffffu, c, m);
@@ -86,7 +93,7 @@ struct Lanes {
   }
   static __device__ __forceinline__ double maxv(double v) {
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
+    for (int m = W / 2; m > 0; m >>= 1) {
       const double o = __shfl_xor_sync(0xffffffffu, v, m);
       v = o > v ? o : v;
     }
@@ -105,79 +112,78 @@ struct Lanes {
   static bool all(bool b) { return b; }
 #endif
 };
-// element i of a length-k vector is handled by lane i (all of them by the host's one lane)
+// element i of a length-k vector is handled by lane i (all of them by the host's one lane);
+// `LN` is the LanesT<W> of the enclosing function
 #if defined(__CUDA_ARCH__)
 #define VSR_UNROLL4 _Pragma("unroll 4")
+#define VSR_FI __forceinline__
 #else
 #define VSR_UNROLL4
+#define VSR_FI inline
 #endif
-#define VSR_FOR_K(i, k) for (int i = Lanes::first(); i < (k); i += Lanes::step())
+#define VSR_FOR_K(i, k) for (int i = LN::first(); i < (k); i += LN::step())
 
 // DCSRCH task codes
 enum { DC_START = 0, DC_FG = 1, DC_CONV = 2, DC_WARN = 3, DC_ERROR = 4 };
 
-struct FitState {
-  int pc;  // resume label of the protothread
-  int k;   // number of constants
+// Scalar state of a run plus ONE pointer to its vector workspace.  16-byte aligned and a
+// multiple of 16 bytes so that a turn moves it between shared memory and registers in
+// 128-bit pieces.
+struct alignas(16) FitState {
+  double* ws;  // [fit_workspace_doubles(k)], see the accessors below
+  int pc;      // resume label of the protothread
+  int k;       // number of constants
   // ---- request / response of one sweep over the points ----
-  double* xe;  // [k] point the sweep must evaluate
-  double rf;   // objective there (scaled, penalty applied)
-  double* rg;  // [k] its gradient (dual mode only)
+  double rf;   // objective at xe() (scaled, penalty applied); its gradient goes to rg() (dual mode)
   // ---- ScalarFunction cache ----
-  double* cx;  // [k] current point of the cache
-  double* cg;  // [k] gradient at cx
   double cf;
   int f_ok, g_ok;
   int nfev, ngev;
   int fd_i;
+  int have_gnew;
   double fd_dx;
-  double* lastx;  // [k] last point the objective was evaluated at (TimedFun.x, bfgs.py:35)
   // ---- BFGS ----
-  double* xk;    // [k]
-  double* gfk;   // [k]
-  double* pk;    // [k]
-  double* xt;    // [k] trial point xk + a*pk
-  double* gnew;  // [k] gradient returned by the line search
-  double* H;     // [k*k] inverse Hessian estimate
-  double* Hy;    // [k] scratch
   int it, maxiter, warnflag, status;
   double old_fval, old_old_fval, gnorm, alpha_k;
-  int have_gnew;
   // ---- line search (shared by wolfe1 and wolfe2) ----
   double phi0, derphi0, old_phi0;
   double stp, phi1, derphi1;
   int task, ls_i, ls_ok;
-  double ls_fval, ls_oldfval;
   // DCSRCH state (_dcsrch.py)
   int brackt, stage;
-  double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1;
   // wolfe2 / zoom
+  int zi, w2_i, zoom_ok, star_has_der, pad0_;
+  double ls_fval, ls_oldfval;
+  double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1;
   double alpha0, alpha1, phi_a0, phi_a1, derphi_a0, derphi_a1;
   double a_lo, a_hi, phi_lo, phi_hi, derphi_lo, a_rec, phi_rec, a_j, phi_aj, derphi_aj;
-  int zi, w2_i, zoom_ok, star_has_der;
   double alpha_star, phi_star;
+  // ---- the vectors, carved from ws (k doubles each, H k*k) ----
+  VSR_HDN double* xe() const { return ws; }              // point the sweep must evaluate
+  VSR_HDN double* rg() const { return ws + k; }          // gradient there (dual mode only)
+  VSR_HDN double* cx() const { return ws + 2 * k; }      // current point of the ScalarFunction cache
+  VSR_HDN double* cg() const { return ws + 3 * k; }      // gradient at cx
+  VSR_HDN double* lastx() const { return ws + 4 * k; }   // last point evaluated (TimedFun.x, bfgs.py:35)
+  VSR_HDN double* xk() const { return ws + 5 * k; }
+  VSR_HDN double* gfk() const { return ws + 6 * k; }
+  VSR_HDN double* pk() const { return ws + 7 * k; }
+  VSR_HDN double* xt() const { return ws + 8 * k; }      // trial point xk + a*pk
+  VSR_HDN double* gnew() const { return ws + 9 * k; }    // gradient returned by the line search
+  VSR_HDN double* Hy() const { return ws + 10 * k; }     // scratch
+  VSR_HDN double* H() const { return ws + 11 * k; }      // [k*k] inverse Hessian estimate
 };
 
 // number of doubles of workspace fit_init() carves for a run with k constants
 VSR_HDN inline int fit_workspace_doubles(int k) { return 11 * k + k * k; }
 
+template <int W = 32>
 VSR_HDN inline void fit_init(FitState& S, int k, double* ws, const double* x0) {
+  using LN = LanesT<W>;
   S.k = k;
-  S.xe = ws;
-  S.rg = ws + k;
-  S.cx = ws + 2 * k;
-  S.cg = ws + 3 * k;
-  S.lastx = ws + 4 * k;
-  S.xk = ws + 5 * k;
-  S.gfk = ws + 6 * k;
-  S.pk = ws + 7 * k;
-  S.xt = ws + 8 * k;
-  S.gnew = ws + 9 * k;
-  S.Hy = ws + 10 * k;
-  S.H = ws + 11 * k;
+  S.ws = ws;
   VSR_FOR_K(i, k) {
-    S.xk[i] = x0[i];
-    S.lastx[i] = x0[i];
+    ws[5 * k + i] = x0[i];  // xk
+    ws[4 * k + i] = x0[i];  // lastx
   }
   S.pc = 0;
   S.f_ok = S.g_ok = 0;
@@ -190,27 +196,27 @@ VSR_HDN inline void fit_init(FitState& S, int k, double* ws, const double* x0) {
 
 namespace detail {
 
-VSR_HDN inline bool finite_d(double x) {
+VSR_HDN VSR_FI bool finite_d(double x) {
 #if defined(__CUDA_ARCH__)
   return isfinite(x);
 #else
   return std::isfinite(x);
 #endif
 }
-VSR_HDN inline bool nan_d(double x) { return x != x; }
-VSR_HDN inline double abs_d(double x) { return ::fabs(x); }
-VSR_HDN inline double max_d(double a, double b) { return b > a ? b : a; }  // python max(a, b): a unless b > a
-VSR_HDN inline double min_d(double a, double b) { return b < a ? b : a; }  // python min(a, b)
-VSR_HDN inline double clip_d(double x, double lo, double hi) {
+VSR_HDN VSR_FI bool nan_d(double x) { return x != x; }
+VSR_HDN VSR_FI double abs_d(double x) { return ::fabs(x); }
+VSR_HDN VSR_FI double max_d(double a, double b) { return b > a ? b : a; }  // python max(a, b): a unless b > a
+VSR_HDN VSR_FI double min_d(double a, double b) { return b < a ? b : a; }  // python min(a, b)
+VSR_HDN VSR_FI double clip_d(double x, double lo, double hi) {
   // np.clip = minimum(maximum(x, lo), hi), nan propagates
   if (nan_d(x)) return x;
   double t = x < lo ? lo : x;
   return t > hi ? hi : t;
 }
-VSR_HDN inline double sign_d(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : (x == 0 ? 0.0 : x)); }
+VSR_HDN VSR_FI double sign_d(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : (x == 0 ? 0.0 : x)); }
 
 // dcstep (_dcsrch.py:502-728): safeguarded cubic/quadratic step of More-Thuente.
-VSR_HDN inline void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy,
+VSR_HDN VSR_FI void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy,
                            double& dy, double& stp, double fp, double dp, int& brackt,
                            double stpmin, double stpmax) {
   const double sgnd = sign_d(dp) * sign_d(dx);
@@ -313,7 +319,7 @@ VSR_HDN inline void dcstep(double& stx, double& fx, double& dx, double& sty, dou
 }
 
 // DCSRCH._iterate (_dcsrch.py:244-500).  ftol = c1, gtol = c2.
-VSR_HDN inline void dcsrch_iterate(FitState& S, double& stp, double f, double g, int& task,
+VSR_HDN VSR_FI void dcsrch_iterate(FitState& S, double& stp, double f, double g, int& task,
                                    double ftol, double gtol, double xtol, double stpmin,
                                    double stpmax) {
   const double p5 = 0.5, p66 = 0.66, xtrapl = 1.1, xtrapu = 4.0;
@@ -350,20 +356,31 @@ VSR_HDN inline void dcsrch_iterate(FitState& S, double& stp, double f, double g,
   if (f <= ftest && abs_d(g) <= gtol * -S.ginit) task = DC_CONV;
   if (task == DC_WARN || task == DC_CONV) return;
 
-  if (S.stage == 1 && f <= S.fx && f > ftest) {
-    const double fm = f - stp * S.gtest;
-    double fxm = S.fx - S.stx * S.gtest;
-    double fym = S.fy - S.sty * S.gtest;
-    const double gm = g - S.gtest;
-    double gxm = S.gx - S.gtest;
-    double gym = S.gy - S.gtest;
+  {
+    // stage 1 works on the modified function psi (f - stp*gtest); one dcstep call site for both
+    // stages (the routine is inlined: two sites doubled the optimiser's code)
+    const bool mod = S.stage == 1 && f <= S.fx && f > ftest;
+    double fm = f, gm = g, fxm = S.fx, fym = S.fy, gxm = S.gx, gym = S.gy;
+    if (mod) {
+      fm = f - stp * S.gtest;
+      fxm = S.fx - S.stx * S.gtest;
+      fym = S.fy - S.sty * S.gtest;
+      gm = g - S.gtest;
+      gxm = S.gx - S.gtest;
+      gym = S.gy - S.gtest;
+    }
     dcstep(S.stx, fxm, gxm, S.sty, fym, gym, stp, fm, gm, S.brackt, S.stmin, S.stmax);
-    S.fx = fxm + S.stx * S.gtest;
-    S.fy = fym + S.sty * S.gtest;
-    S.gx = gxm + S.gtest;
-    S.gy = gym + S.gtest;
-  } else {
-    dcstep(S.stx, S.fx, S.gx, S.sty, S.fy, S.gy, stp, f, g, S.brackt, S.stmin, S.stmax);
+    if (mod) {
+      S.fx = fxm + S.stx * S.gtest;
+      S.fy = fym + S.sty * S.gtest;
+      S.gx = gxm + S.gtest;
+      S.gy = gym + S.gtest;
+    } else {
+      S.fx = fxm;
+      S.fy = fym;
+      S.gx = gxm;
+      S.gy = gym;
+    }
   }
   if (S.brackt) {
     if (abs_d(S.sty - S.stx) >= p66 * S.width1) stp = S.stx + p5 * (S.sty - S.stx);
@@ -385,7 +402,7 @@ VSR_HDN inline void dcsrch_iterate(FitState& S, double& stp, double f, double g,
 }
 
 // _cubicmin / _quadmin (_linesearch.py): a non-finite result means "None".
-VSR_HDN inline bool cubicmin(double a, double fa, double fpa, double b, double fb, double c,
+VSR_HDN VSR_FI bool cubicmin(double a, double fa, double fpa, double b, double fb, double c,
                              double fc, double& xmin) {
   const double C = fpa;
   const double db = b - a, dc = c - a;
@@ -401,7 +418,7 @@ VSR_HDN inline bool cubicmin(double a, double fa, double fpa, double b, double f
   xmin = a + (-B + ::sqrt(radical)) / (3 * A);
   return finite_d(xmin);
 }
-VSR_HDN inline bool quadmin(double a, double fa, double fpa, double b, double fb, double& xmin) {
+VSR_HDN VSR_FI bool quadmin(double a, double fa, double fpa, double b, double fb, double& xmin) {
   const double D = fa, C = fpa;
   const double db = b - a * 1.0;
   if (db * db == 0.0) return false;
@@ -417,6 +434,7 @@ VSR_HDN inline bool quadmin(double a, double fa, double fpa, double b, double fb
 #define VSR_CO_YIELD_(S, n)   \
   do {                        \
     (S).pc = (n) + 1;         \
+    G_ = (S);                 \
     return VSR_NEED_EVAL;     \
     case (n) + 1:;            \
   } while (0)
@@ -427,10 +445,10 @@ VSR_HDN inline bool quadmin(double a, double fa, double fpa, double b, double fb
   do {                                                             \
     bool same_ = true;                                             \
     VSR_FOR_K(i_, (S).k)                                           \
-    if (!((xptr)[i_] == (S).cx[i_])) same_ = false;                \
-    same_ = Lanes::all(same_);                                     \
+    if (!((xptr)[i_] == v_cx[i_])) same_ = false;                \
+    same_ = LN::all(same_);                                     \
     if (!same_) {                                                  \
-      VSR_FOR_K(i_, (S).k)(S).cx[i_] = (xptr)[i_];                 \
+      VSR_FOR_K(i_, (S).k)v_cx[i_] = (xptr)[i_];                 \
       (S).f_ok = 0;                                                \
       (S).g_ok = 0;                                                \
     }                                                              \
@@ -440,14 +458,14 @@ VSR_HDN inline bool quadmin(double a, double fa, double fpa, double b, double fb
 #define VSR_OBJ_UPDATE_FUN(S, O)                                   \
   do {                                                             \
     if (!(S).f_ok) {                                               \
-      VSR_FOR_K(i_, (S).k)(S).xe[i_] = (S).cx[i_];                 \
+      VSR_FOR_K(i_, (S).k)v_xe[i_] = v_cx[i_];                 \
       VSR_CO_YIELD(S);                                             \
       (S).cf = (S).rf;                                             \
       (S).nfev += 1;                                               \
       (S).f_ok = 1;                                                \
-      VSR_FOR_K(i_, (S).k)(S).lastx[i_] = (S).xe[i_];              \
+      VSR_FOR_K(i_, (S).k)v_lastx[i_] = v_xe[i_];              \
       if ((O).grad_mode == VSR_GRAD_DUAL) {                        \
-        VSR_FOR_K(i_, (S).k)(S).cg[i_] = (S).rg[i_];               \
+        VSR_FOR_K(i_, (S).k)v_cg[i_] = v_rg[i_];               \
         (S).g_ok = 1;                                              \
         (S).ngev += 1;                                             \
       }                                                            \
@@ -462,20 +480,20 @@ VSR_HDN inline bool quadmin(double a, double fa, double fpa, double b, double fb
       if (!(S).g_ok) {                                                               \
         for ((S).fd_i = 0; (S).fd_i < (S).k; ++(S).fd_i) {                           \
           {                                                                          \
-            Lanes::sync(); /* cx[fd_i] was written by its owner lane */              \
-            const double x_ = (S).cx[(S).fd_i];                                      \
+            LN::sync(); /* cx[fd_i] was written by its owner lane */              \
+            const double x_ = v_cx[(S).fd_i];                                      \
             double h_ = (O).fd_eps;                                                  \
             if ((x_ + h_) - x_ == 0.0) {                                             \
               const double a_ = ::fabs(x_) > 1.0 ? ::fabs(x_) : 1.0;                 \
               h_ = 1.4901161193847656e-08 * (x_ >= 0 ? 1.0 : -1.0) * a_;             \
             }                                                                        \
             (S).fd_dx = (x_ + h_) - x_;                                              \
-            VSR_FOR_K(i_, (S).k)(S).xe[i_] = (i_ == (S).fd_i) ? x_ + h_ : (S).cx[i_]; \
+            VSR_FOR_K(i_, (S).k)v_xe[i_] = (i_ == (S).fd_i) ? x_ + h_ : v_cx[i_]; \
           }                                                                          \
           VSR_CO_YIELD(S);                                                           \
           VSR_FOR_K(i_, (S).k) {                                                     \
-            if (i_ == (S).fd_i) (S).cg[i_] = ((S).rf - (S).cf) / (S).fd_dx;          \
-            (S).lastx[i_] = (S).xe[i_];                                              \
+            if (i_ == (S).fd_i) v_cg[i_] = ((S).rf - (S).cf) / (S).fd_dx;          \
+            v_lastx[i_] = v_xe[i_];                                              \
           }                                                                          \
           (S).nfev += 1;                                                             \
         }                                                                            \
@@ -490,37 +508,52 @@ VSR_HDN inline bool quadmin(double a, double fa, double fpa, double b, double fb
 // uses so the ScalarFunction cache hits exactly when scipy's does.
 #define VSR_LS_PHI(S, O, a, out)                                                  \
   do {                                                                            \
-    VSR_FOR_K(i_, (S).k)(S).xt[i_] = (S).xk[i_] + (a) * (S).pk[i_];               \
-    VSR_OBJ_SETX(S, (S).xt);                                                      \
+    VSR_FOR_K(i_, (S).k)v_xt[i_] = v_xk[i_] + (a) * v_pk[i_];               \
+    VSR_OBJ_SETX(S, v_xt);                                                      \
     VSR_OBJ_UPDATE_FUN(S, O);                                                     \
     (out) = (S).cf;                                                               \
   } while (0)
 #define VSR_LS_DERPHI(S, O, a, out)                                               \
   do {                                                                            \
-    VSR_FOR_K(i_, (S).k)(S).xt[i_] = (S).xk[i_] + (a) * (S).pk[i_];               \
-    VSR_OBJ_SETX(S, (S).xt);                                                      \
+    VSR_FOR_K(i_, (S).k)v_xt[i_] = v_xk[i_] + (a) * v_pk[i_];               \
+    VSR_OBJ_SETX(S, v_xt);                                                      \
     VSR_OBJ_UPDATE_GRAD(S, O);                                                    \
     {                                                                             \
       double d_ = 0.0;                                                            \
       VSR_FOR_K(i_, (S).k) {                                                      \
-        (S).gnew[i_] = (S).cg[i_];                                                \
-        d_ += (S).cg[i_] * (S).pk[i_];                                            \
+        v_gnew[i_] = v_cg[i_];                                                \
+        d_ += v_cg[i_] * v_pk[i_];                                            \
       }                                                                           \
       (S).have_gnew = 1;                                                          \
-      (out) = Lanes::sum(d_);                                                     \
+      (out) = LN::sum(d_);                                                     \
     }                                                                             \
   } while (0)
 
 // Advance the run.  Returns VSR_NEED_EVAL when the caller must evaluate the objective
-// at S.xe (store it in S.rf, and its gradient in S.rg in dual mode), VSR_DONE when
-// finished (result: S.xk, S.old_fval, S.status, S.it, S.nfev, S.lastx).
-VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
+// at S.xe() (store it in S.rf, and its gradient in S.rg() in dual mode), VSR_DONE when
+// finished (result: S.xk(), S.old_fval, S.status, S.it, S.nfev, S.lastx()).
+template <int W = 32>
+VSR_HDN VSR_FI int fit_step(FitState& G_, const FitOpts& O) {
   using namespace detail;
+  using LN = LanesT<W>;
+  FitState S = G_;  // private copy: registers (and an L1-resident stack) for the length of the turn
   const int k = S.k;
+  double* const v_xe = S.ws;
+  double* const v_rg = S.ws + k;
+  double* const v_cx = S.ws + 2 * k;
+  double* const v_cg = S.ws + 3 * k;
+  double* const v_lastx = S.ws + 4 * k;
+  double* const v_xk = S.ws + 5 * k;
+  double* const v_gfk = S.ws + 6 * k;
+  double* const v_pk = S.ws + 7 * k;
+  double* const v_xt = S.ws + 8 * k;
+  double* const v_gnew = S.ws + 9 * k;
+  double* const v_Hy = S.ws + 10 * k;
+  double* const v_H = S.ws + 11 * k;
   switch (S.pc) {
     case 0:
       // ScalarFunction.__init__: f and grad at x0
-      VSR_FOR_K(i, k) S.cx[i] = S.xk[i];
+      VSR_FOR_K(i, k) v_cx[i] = v_xk[i];
       S.f_ok = S.g_ok = 0;
       VSR_OBJ_UPDATE_FUN(S, O);
       VSR_OBJ_UPDATE_GRAD(S, O);
@@ -531,16 +564,16 @@ VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
         double n2 = 0.0, gm = 0.0;
         bool gnan = false;
         VSR_FOR_K(i, k) {
-          const double gi = S.cg[i];
-          S.gfk[i] = gi;
-          for (int j = 0; j < k; ++j) S.H[i * k + j] = (i == j) ? 1.0 : 0.0;
+          const double gi = v_cg[i];
+          v_gfk[i] = gi;
+          for (int j = 0; j < k; ++j) v_H[i * k + j] = (i == j) ? 1.0 : 0.0;
           n2 += gi * gi;
           if (nan_d(gi)) gnan = true;
           if (abs_d(gi) > gm) gm = abs_d(gi);
         }
-        n2 = Lanes::sum(n2);
-        gm = Lanes::maxv(gm);
-        gnan = Lanes::any(gnan);
+        n2 = LN::sum(n2);
+        gm = LN::maxv(gm);
+        gnan = LN::any(gnan);
         S.old_old_fval = S.old_fval + ::sqrt(n2) / 2;
         S.gnorm = gnan ? ::nan("") : gm;  // vecnorm(gfk, inf) = amax(|gfk|), nan propagates
       }
@@ -548,17 +581,17 @@ VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
 
       while (S.gnorm > O.gtol && S.it < S.maxiter) {
         // pk = -Hk . gfk   (row i on lane i)
-        Lanes::sync();
+        LN::sync();
         {
           double d = 0.0;
           VSR_FOR_K(i, k) {
             double acc = 0.0;
             VSR_UNROLL4
-            for (int j = 0; j < k; ++j) acc += S.H[i * k + j] * S.gfk[j];
-            S.pk[i] = -acc;
-            d += S.gfk[i] * -acc;
+            for (int j = 0; j < k; ++j) acc += v_H[i * k + j] * v_gfk[j];
+            v_pk[i] = -acc;
+            d += v_gfk[i] * -acc;
           }
-          S.derphi0 = Lanes::sum(d);
+          S.derphi0 = LN::sum(d);
         }
         // ---------------- line_search_wolfe1 ----------------
         S.phi0 = S.old_fval;
@@ -597,7 +630,7 @@ VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
           S.ls_fval = S.phi1;
           S.ls_oldfval = S.phi0;
           // gval[0]: gradient of the last derphi call (gfk when there was none)
-          if (!S.have_gnew) VSR_FOR_K(i, k) S.gnew[i] = S.gfk[i];
+          if (!S.have_gnew) VSR_FOR_K(i, k) v_gnew[i] = v_gfk[i];
           S.have_gnew = 1;
         } else {
           // ---------------- line_search_wolfe2 (fallback) ----------------
@@ -750,32 +783,32 @@ VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
 #endif
         // xkp1 = xk + alpha_k*pk
         VSR_FOR_K(i, k) {
-          S.Hy[i] = S.alpha_k * S.pk[i];  // sk (kept in Hy until the update below)
-          S.xt[i] = S.xk[i] + S.Hy[i];
+          v_Hy[i] = S.alpha_k * v_pk[i];  // sk (kept in Hy until the update below)
+          v_xt[i] = v_xk[i] + v_Hy[i];
         }
         if (!S.have_gnew) {
-          VSR_OBJ_SETX(S, S.xt);
+          VSR_OBJ_SETX(S, v_xt);
           VSR_OBJ_UPDATE_GRAD(S, O);
-          VSR_FOR_K(i, k) S.gnew[i] = S.cg[i];
+          VSR_FOR_K(i, k) v_gnew[i] = v_cg[i];
         }
         {
           double gm = 0.0, pn2 = 0.0, xn2 = 0.0, ys = 0.0;
           bool gnan = false;
           VSR_FOR_K(i, k) {
-            pn2 += S.pk[i] * S.pk[i];
-            const double yi = S.gnew[i] - S.gfk[i];
-            S.pk[i] = yi;  // yk (pk is free until the next iteration)
-            S.gfk[i] = S.gnew[i];
-            S.xk[i] = S.xt[i];
-            xn2 += S.xk[i] * S.xk[i];
-            ys += yi * S.Hy[i];
-            if (nan_d(S.gfk[i])) gnan = true;
-            if (abs_d(S.gfk[i]) > gm) gm = abs_d(S.gfk[i]);
+            pn2 += v_pk[i] * v_pk[i];
+            const double yi = v_gnew[i] - v_gfk[i];
+            v_pk[i] = yi;  // yk (pk is free until the next iteration)
+            v_gfk[i] = v_gnew[i];
+            v_xk[i] = v_xt[i];
+            xn2 += v_xk[i] * v_xk[i];
+            ys += yi * v_Hy[i];
+            if (nan_d(v_gfk[i])) gnan = true;
+            if (abs_d(v_gfk[i]) > gm) gm = abs_d(v_gfk[i]);
           }
-          Lanes::sum3(pn2, xn2, ys);
+          LN::sum3(pn2, xn2, ys);
           const double rhok_inv = ys;
-          gm = Lanes::maxv(gm);
-          gnan = Lanes::any(gnan);
+          gm = LN::maxv(gm);
+          gnan = LN::any(gnan);
           S.it += 1;
           S.gnorm = gnan ? ::nan("") : gm;
           if (S.gnorm <= O.gtol) break;
@@ -789,37 +822,37 @@ VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
           // evaluated as the two products scipy forms, using their rank-one structure:
           //   T = H A2      = H - rho (H y) s^T        (row i on lane i)
           //   A1 T          = T - rho s (y^T T)        (column sums on lane j, rows on lane i)
-          const double* sk = S.Hy;
-          const double* yk = S.pk;
+          const double* sk = v_Hy;
+          const double* yk = v_pk;
           const double rhok = (rhok_inv == 0.0) ? 1000.0 : 1.0 / rhok_inv;
-          double* w = S.xt;  // free until the next line search
-          Lanes::sync();     // yk, sk complete
+          double* w = v_xt;  // free until the next line search
+          LN::sync();     // yk, sk complete
           VSR_FOR_K(i, k) {
             double ui = 0.0;
             VSR_UNROLL4
-            for (int j = 0; j < k; ++j) ui += S.H[i * k + j] * yk[j];
+            for (int j = 0; j < k; ++j) ui += v_H[i * k + j] * yk[j];
             VSR_UNROLL4
-            for (int j = 0; j < k; ++j) S.H[i * k + j] -= rhok * ui * sk[j];
+            for (int j = 0; j < k; ++j) v_H[i * k + j] -= rhok * ui * sk[j];
           }
-          Lanes::sync();  // T complete
+          LN::sync();  // T complete
           VSR_FOR_K(j, k) {
             double a2 = 0.0;
             VSR_UNROLL4
-            for (int l = 0; l < k; ++l) a2 += yk[l] * S.H[l * k + j];
+            for (int l = 0; l < k; ++l) a2 += yk[l] * v_H[l * k + j];
             w[j] = a2;
           }
-          Lanes::sync();  // w complete
+          LN::sync();  // w complete
           VSR_FOR_K(i, k) {
             VSR_UNROLL4
-            for (int j = 0; j < k; ++j) S.H[i * k + j] += rhok * sk[i] * sk[j] - rhok * sk[i] * w[j];
+            for (int j = 0; j < k; ++j) v_H[i * k + j] += rhok * sk[i] * sk[j] - rhok * sk[i] * w[j];
           }
         }
       }
       // ---- termination message (_optimize.py:1503-1513) ----
       {
         bool xnan = false;
-        VSR_FOR_K(i, k) if (nan_d(S.xk[i])) xnan = true;
-        xnan = Lanes::any(xnan);
+        VSR_FOR_K(i, k) if (nan_d(v_xk[i])) xnan = true;
+        xnan = LN::any(xnan);
         if (S.warnflag == 2)
           S.status = VSR_FIT_PRECLOSS;
         else if (S.it >= S.maxiter)
@@ -830,6 +863,7 @@ VSR_HDN inline int fit_step(FitState& S, const FitOpts& O) {
           S.status = VSR_FIT_SUCCESS;
       }
       S.pc = -1;
+      G_ = S;
       return VSR_DONE;
     default:
       return VSR_DONE;

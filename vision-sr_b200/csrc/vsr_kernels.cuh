@@ -61,19 +61,18 @@ struct FitArgs {
   int32_t resident;      // 1: every CTA stages its slice of the points into shared memory
   int32_t tma_ok;        // 1: column starts and strides are 16-byte aligned (bulk copies)
   int32_t slice_stride;  // elements between columns of the staged slice
-  int32_t seats;         // runs in flight per cluster (<= warps per CTA, <= kMaxSeats)
-  int32_t banks;         // 2: optimiser steps of one half of the seats overlap the sweeps of the other
-  int32_t reserved;      // warps of the leader CTA that never sweep (0 or 2), see choose_geometry
+  int32_t seats;         // runs in flight per cluster (<= kMaxSeats)
+  int32_t reserved;      // warps of the leader CTA that run optimiser turns and never sweep (0: the
+                         // optimiser warps sweep as well), see choose_geometry
   // seat layout in doubles, computed once on the host (fit_seat_layout): the kernel would
-  // otherwise re-derive it from (kmax, K, warps, cluster size, ...) at every use
-  int32_t seat_d, off_cred, off_cst, off_imm, off_insn;
+  // otherwise re-derive it from (kmax, K, cluster size, ...) at every use
+  int32_t seat_d, off_cred, off_ctrl, off_insn;
   int32_t kmax, max_insn, max_imm;  // maxima over this launch's programs (size the seat areas)
   int32_t n_cols;                   // columns of X this launch's programs read
   int32_t col_of_var[VSR_MAX_VARS]; // slice column of variable j (-1: unused)
   int32_t* queue;           // [1] index of the next run to hand out (zeroed by the host)
-  long long* phase_cycles;  // optional [n_slots][8]: cycles of the seat's optimiser lane 0:
-                            // [0] optimiser logic, [3] everything else while seated, [7] passes; runs of seat 0 also
-                            // carry the cluster's [1] barrier 1 [2] fetch [4] sweeps [5] barrier 2
+  long long* phase_cycles;  // optional [n_slots][8]: cycles of the run's optimiser lane 0:
+                            // [0] optimiser turns, [3] everything else while seated, [7] passes
   FitOpts O;
 };
 
@@ -224,7 +223,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-// ---- TMA (bulk async copy) + mbarrier primitives, sm_90+ PTX ------------------------------
+// ---- TMA (bulk async copy), mbarrier and cluster async-store primitives, sm_90+ PTX -----------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -238,6 +237,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// blocks until the phase with the given parity has completed (hardware-suspended wait, SASS SYNCS...TRYWAIT)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -251,6 +251,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// non-blocking probe of a phase
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // global -> this CTA's shared memory, completion counted in bytes on `bar` (SASS: UBLKCP)
 __device__ __forceinline__ void tma_bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes,
                                               uint64_t* bar) {
@@ -259,6 +273,35 @@ __device__ __forceinline__ void tma_bulk_load(void* dst_smem, const void* src_gm
           smem_u32(dst_smem)),
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+// shared::cluster address of this CTA's shared-memory address `a` in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t a, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+// one arrival + `bytes` more expected transaction bytes on a barrier of ANY CTA of the cluster
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes)
+               : "memory");
+}
+// asynchronous store into the shared memory of a CTA of the cluster; the store's bytes are counted
+// on a barrier of the SAME CTA, whose waiters see the data once the phase completes
+__device__ __forceinline__ void st_async_b64(uint32_t dst_cluster_addr, uint64_t v, uint32_t bar_cluster_addr) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst_cluster_addr),
+               "l"(v), "r"(bar_cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_b32(uint32_t dst_cluster_addr, uint32_t v, uint32_t bar_cluster_addr) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst_cluster_addr),
+               "r"(v), "r"(bar_cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_val(uint32_t dst, double v, uint32_t bar) {
+  st_async_b64(dst, (uint64_t)__double_as_longlong(v), bar);
+}
+__device__ __forceinline__ void st_async_val(uint32_t dst, float v, uint32_t bar) {
+  st_async_b32(dst, __float_as_uint(v), bar);
 }
 
 // ---- point source: this CTA's slice, resident in shared memory ----------------------------------
@@ -326,72 +369,142 @@ __device__ __forceinline__ void sweep_slice(const vsr_insn_t* prog, const double
   }
 }
 
+// ---- warp reduction of NC values per lane --------------------------------------------------------
+// Recursive halving: at the level with lane distance m, the lanes with (lane & m) == 0 keep the
+// first half of their values and receive the partner's copy of them, the others the second half.
+// After log2(n) levels each lane holds ONE value; the remaining levels are a plain butterfly.
+// n + (5 - log2 n) double shuffles instead of 5 n.  Fixed order: the result depends on nothing
+// but the values.  On return v[0] of every lane is the total of component reduce_comp<N>(lane).
+template <int N>  // N: power of two, 1..32
+__device__ __forceinline__ void warp_reduce_pow2(double (&v)[N], int lane) {
+  int m = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1) {
+    const bool upper = (lane & m) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const double send = upper ? v[i] : v[i + n / 2];
+      const double keep = upper ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+    m >>= 1;
+  }
+#pragma unroll
+  for (; m > 0; m >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
+}
+template <int N>
+__device__ __forceinline__ int reduce_comp(int lane) {
+  int c = 0, m = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1) {
+    if (lane & m) c += n / 2;
+    m >>= 1;
+  }
+  return c;
+}
+__host__ __device__ constexpr int pow2_floor(int n) { return n >= 32 ? 32 : n >= 16 ? 16 : n >= 8 ? 8 : n >= 4 ? 4 : n >= 2 ? 2 : 1; }
+__host__ __device__ constexpr int pow2_ceil(int n) { return n > 16 ? 32 : n > 8 ? 16 : n > 4 ? 8 : n > 2 ? 4 : n > 1 ? 2 : 1; }
+
+// Sums the K+1 per-thread partial sums of a sweep (scratch: [(K+1)][snt], this thread's column
+// stid) over the warp and stores the warp's totals to out[0..K].
+template <int K>
+__device__ __forceinline__ void warp_totals(const double* scratch, int stid, int snt, int lane, double* out) {
+  constexpr int NC = K + 1;
+  // NC = 2^j + 1 (2, 3, 5, 9, 17): the 2^j block by halving, the odd one out by a plain butterfly;
+  // otherwise pad to the next power of two
+  constexpr bool odd_one = NC > 1 && pow2_floor(NC) + 1 == NC;
+  constexpr int NB = odd_one ? pow2_floor(NC) : pow2_ceil(NC);
+  double v[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) v[c] = c < NC ? scratch[c * snt + stid] : 0.0;
+  warp_reduce_pow2<NB>(v, lane);
+  const int comp = reduce_comp<NB>(lane);
+  constexpr int low = 32 / NB - 1;  // lanes that share a component differ in these bits
+  if ((lane & low) == 0 && comp < NC) out[comp] = v[0];
+  if (odd_one) {
+    double w = scratch[(NC - 1) * snt + stid];
+    w = warp_sum(w);
+    if (lane == 0) out[NC - 1] = w;
+  }
+}
+
 // ---- fit kernel ------------------------------------------------------------------------------------
-// PERSISTENT thread-block clusters, each working on `seats` (candidate, restart) runs at a time.
+// PERSISTENT thread-block clusters, each working on `seats` (candidate, restart) runs at a time, as a
+// DATAFLOW of point-to-point messages through distributed shared memory -- no cluster-wide or
+// CTA-wide barrier between the one that starts the kernel and the one that ends it.
 //
-// A pass of one run is: optimiser step (one warp, 16-21 k cycles of dependent scalar work) ->
-// sweep of all points through the interpreter (all warps of all CTAs) -> reduction.  With one run
-// per cluster every warp but one idles through the optimiser step and the cluster barriers
-// (ncu: two thirds of all warp samples sat in barrier waits).  Here a cluster holds G runs in
-// "seats", split in two banks: while the optimiser turns of one bank run on reserved warps of the
-// leader CTA, all other warps sweep the requests of the other bank back to back (the schedule is
-// described at the loop below).  A seat whose run finishes takes the next run from the launch's
-// queue (one atomic), so seats stay full until the queue drains; the last long runs then have
-// their cluster to themselves and advance at single-run latency.
+// A pass of one run is: optimiser turn (one warp: take in the totals, advance the BFGS state machine
+// to its next request) -> sweep of all points through the interpreter (every sweeper warp of every CTA)
+// -> reduction.  The run of seat g moves through these stations by messages:
+//
+//   REQUEST  the seat's optimiser warp (leader CTA) writes (program id, k, trial constants -- and the
+//            predecoded program itself when the run is new) into the seat area of EVERY CTA with
+//            st.async; the bytes are counted on that CTA's request barrier req_bar[g], so a sweeper
+//            warp that sees the phase complete sees the whole request.
+//   SWEEP    every sweeper warp polls the request barriers of the seats; a warp that finds a request
+//            evaluates ITS points for it, reduces its K+1 partial sums over the warp (shuffles) and
+//            parks them; the last warp of the CTA to finish (a shared-memory ticket) adds the warps'
+//            partials in warp order and sends the CTA's K+1 sums to the leader with st.async, counted
+//            on the leader's part_bar[g].
+//   TOTALS   the optimiser warp wakes when all CTAs have reported, adds them in rank order, and
+//            runs its turn.
+//
+// Warps never wait for each other: while one seat's optimiser turn runs (5-20 k cycles of dependent
+// scalar work) the sweepers serve the other seats, and a warp that finishes a sweep early starts the
+// next seat's.  A seat whose run finishes takes the next run from the launch's queue (one atomic)
+// inside the same turn; when the queue is drained the seat's optimiser sends a last request with
+// program id -1 and the sweepers stop polling it.  The last long runs then have the cluster to
+// themselves and a pass costs: turn + two DSMEM hops + one sweep.
 //
 // The points are split in contiguous slices, one per CTA.  When a slice fits, the columns the
-// launch's programs read and y are staged ONCE per cluster into shared memory by TMA bulk
-// copies and stay there for every pass of every run the cluster handles.  Reduction order is
-// fixed (lanes, warps, CTA rank), so a run's result does not depend on its seat or cluster.
+// launch's programs read and y are staged ONCE per cluster into shared memory by TMA bulk copies and
+// stay there for every pass of every run the cluster handles.  Reduction order is fixed (lanes,
+// warps, CTA rank), so a run's result does not depend on its seat, its cluster or the other runs.
 //
-// dynamic shared memory (doubles):  per seat [ FitState | ws | cred[cs*(K+1)] | cst | imm | insn ]
-//   then the reduction scratch [(K+1)][threads], then the slice: (n_cols + 1) * stride * sizeof(T)
-// The optimiser state of a seat lives in SHARED memory, one copy per seat that all 32 lanes of
-// the seat's warp read (broadcast) and write (same value, uniform control flow).  As a per-lane
-// local variable it was evicted from L1 by every sweep's spill and operand-stack traffic, and
-// each pass re-read it from L2: 18-21 k cycles per optimiser step on an otherwise idle SM.
+// dynamic shared memory (doubles):
+//   per seat [ FitState | ws | cred[cs*(K+1)] | ctrl (16 B) | cst | imm | insn ]
+//   then wpart [seats][warps][K+1], the per-thread scratch [(K+1)][threads], then the slice
+//   (n_cols + 1) * stride * sizeof(T).
+// FitState / ws / cred are used in the leader CTA only; the layout is the same in every CTA so that
+// one offset addresses the same thing cluster-wide (mapa).
 constexpr int kFitStateDoubles = (int)((sizeof(FitState) + 15) / 16 * 2);
-// The code area of a seat is  cst[kSeatCstDoubles] | imm[VSR_MAX_IMMS] | insn[...]  with FIXED sizes
-// in front of the instructions, so that the interpreter addresses constants, literals and
-// instruction words at compile-time offsets from ONE register (see the sweep call sites).
+// The code area of a seat is  ctrl[2] | cst[kSeatCstDoubles] | imm[VSR_MAX_IMMS] | insn[...]  with FIXED
+// sizes in front of the instructions, so that the interpreter addresses constants, literals and
+// instruction words at compile-time offsets from ONE register (see the sweep call site).
 constexpr int kSeatCstDoubles = VSR_MAX_CONSTS + 2;
+constexpr int kSeatCtrlDoubles = 2;
 
-__host__ __device__ inline size_t fit_seat_doubles(int kmax, int K, int nwarps, int cs, int max_insn,
-                                                   int max_imm) {
-  size_t d = kFitStateDoubles + (size_t)fit_workspace_doubles(kmax) + (size_t)cs * (K + 1) +
+__host__ __device__ inline size_t fit_seat_doubles(int kmax, int K, int cs, int max_insn) {
+  size_t d = kFitStateDoubles + (size_t)fit_workspace_doubles(kmax) + (size_t)cs * (K + 1) + kSeatCtrlDoubles +
              kSeatCstDoubles + VSR_MAX_IMMS + max_insn + 1;  // + pad word after END
-  (void)nwarps;
   return (d + 1) & ~(size_t)1;  // 16-byte multiple
 }
 // offsets (in doubles) of the parts of a seat, and the seat's size
 struct SeatLayout {
-  int seat_d, off_ws, off_cred, off_cst, off_imm, off_insn;
+  int seat_d, off_ws, off_cred, off_ctrl, off_cst, off_imm, off_insn;
 };
-__host__ __device__ inline SeatLayout fit_seat_layout(int kmax, int K, int nwarps, int cs, int max_insn,
-                                                      int max_imm) {
+__host__ __device__ inline SeatLayout fit_seat_layout(int kmax, int K, int cs, int max_insn) {
   SeatLayout L;
   L.off_ws = kFitStateDoubles;
   L.off_cred = L.off_ws + fit_workspace_doubles(kmax);
-  L.off_cst = L.off_cred + cs * (K + 1);
+  L.off_ctrl = L.off_cred + cs * (K + 1);
+  L.off_cst = L.off_ctrl + kSeatCtrlDoubles;
   L.off_imm = L.off_cst + kSeatCstDoubles;
   L.off_insn = L.off_imm + VSR_MAX_IMMS;
-  L.seat_d = (int)fit_seat_doubles(kmax, K, nwarps, cs, max_insn, max_imm);
+  L.seat_d = (int)fit_seat_doubles(kmax, K, cs, max_insn);
   return L;
 }
 
-__host__ __device__ inline size_t fit_smem_bytes(int seats, int kmax, int K, int nwarps, int cs,
-                                                 int max_insn, int max_imm, int n_cols, int stride,
-                                                 int elem) {
-  return (size_t)seats * fit_seat_doubles(kmax, K, nwarps, cs, max_insn, max_imm) * 8 +
-         (size_t)(K + 1) * nwarps * 32 * 8 +  // reduction scratch of block_totals
+__host__ __device__ inline size_t fit_smem_bytes(int seats, int kmax, int K, int nwarps, int cs, int max_insn,
+                                                 int n_cols, int stride, int elem) {
+  return (size_t)seats * fit_seat_doubles(kmax, K, cs, max_insn) * 8 +
+         (size_t)seats * nwarps * (K + 1) * 8 +  // wpart
+         (size_t)(K + 1) * nwarps * 32 * 8 +     // per-thread scratch of the sweeps
          (n_cols >= 0 ? (size_t)(n_cols + 1) * stride * elem : 0);
 }
 
 // Widest CTA the fit kernel is compiled for: ONE CTA of 640 threads (20 warps at <= 96
-// registers) per SM, so a cluster owns its SMs.  Measured on the BASELINE config-2 beams
-// (tools/exp_schedules.py, us per 1000 sweeps): 8 CTAs x 640 threads 1034, 16 x 320 with two CTAs
-// per SM 1106, 16 x 160 with four 1070: optimiser steps run uncontended and a sweep of
-// N = 10 000 is one tile iteration.
+// registers) per SM, so a cluster owns its SMs.
 #if !defined(VSR_FIT_THREADS)
 #define VSR_FIT_THREADS 640
 #define VSR_FIT_MINCTAS 1
@@ -404,39 +517,99 @@ template <typename T, int K>
 __host__ __device__ constexpr int fit_min_ctas() {
   return (sizeof(T) == 8 && K > 8) ? 1 : VSR_FIT_MINCTAS;
 }
+// lanes that own vector elements in the optimiser turn of a width-K kernel (k <= K; the width-0
+// kernel also runs the forward-difference mode, any k <= 32)
+template <int K>
+__host__ __device__ constexpr int fit_lanes() {
+  return K == 0 ? 32 : (K <= 8 ? 8 : 16);
+}
 
 // The optimiser step, out of line: its register and stack needs stay out of the sweep's
 // allocation (the sweep is the hot loop; this runs on one warp per seat between sweeps).
-static __device__ __noinline__ int fit_step_call(FitState& S, const FitOpts& O) { return fit_step(S, O); }
+template <int W>
+static __device__ __noinline__ int fit_step_call(FitState& S, const FitOpts& O) {
+  return fit_step<W>(S, O);
+}
 
+// request header of a seat, 16 bytes, written by the seat's optimiser into every CTA
 struct SeatCtrl {
-  int prog;     // program of the seated run, -1: seat empty
-  int k;        // its number of constants
-  int fresh;    // 1: the run was seated in its optimiser's last turn (every CTA must load its program)
-  int drained;  // 1: the seat's optimiser found the launch's queue empty
+  int prog;  // program of the seated run, -1: the seat is closed (queue drained)
+  int k;     // its number of constants
+  int n_insn, pad;
 };
 
 // what the optimiser warp of a seat carries from one turn to the next (leader CTA only)
 struct SeatBook {
-  int slot;                     // output row of the seated run
+  int slot;  // output row of the seated run
+  int prog;  // its program, -1: seat empty
+  int k;
   int pad;
-  unsigned long long t0;        // TimedFun clock (bfgs.py:29-33)
-  double rf;                    // scratch: lane 0 -> all lanes
+  unsigned long long t0;  // TimedFun clock (bfgs.py:29-33)
+  double rf;              // scratch: lane 0 -> all lanes
   long long t_logic, t_seated, n_pass;  // phase_cycles bookkeeping
 };
 
-// One optimiser turn of seat `seat`, run by ONE warp of the leader CTA (any warp: all of the
-// seat's state is in shared memory): take in the totals of the sweep that served the seat's last
-// request, advance the run to its next request, and when it finishes write its results and seat
-// the next run of the launch's queue.  Publishes the seat table entry the sweepers read in the
-// next iteration.
+// Sends the request of seat `seat` to every CTA of the cluster.  `fresh`: the program goes along
+// (predecoded, VAR operands rewritten to slice columns when the slices are resident).
+template <typename T>
+__device__ __forceinline__ void publish_request(const FitArgs& a, int cs, int lane, int prog, int k, bool fresh,
+                                                const double* xe, uint32_t ctrl_addr, uint32_t req_bar_addr) {
+  int i0 = 0, ni = 0, m0 = 0, nm = 0;
+  if (prog >= 0 && fresh) {
+    i0 = a.pt.insn_off[prog];
+    ni = a.pt.insn_off[prog + 1] - i0;
+    m0 = a.pt.imm_off[prog];
+    nm = a.pt.imm_off[prog + 1] - m0;
+  }
+  const uint32_t bytes = 16u + (prog >= 0 ? (uint32_t)k * (uint32_t)sizeof(T) : 0u) +
+                         (fresh && prog >= 0 ? (uint32_t)(nm + ni + 1) * 8u : 0u);
+  for (int r = lane; r < cs; r += 32) mbar_expect_tx_cluster(mapa_u32(req_bar_addr, r), bytes);
+  // header
+  if (lane < 2) {
+    const uint64_t w = lane == 0 ? ((uint64_t)(uint32_t)prog | ((uint64_t)(uint32_t)k << 32)) : (uint64_t)(uint32_t)ni;
+    for (int r = 0; r < cs; ++r) st_async_b64(mapa_u32(ctrl_addr + 8u * lane, r), w, mapa_u32(req_bar_addr, r));
+  }
+  if (prog < 0) return;
+  // trial constants in the sweep's arithmetic type
+  const uint32_t cst_addr = ctrl_addr + 8u * kSeatCtrlDoubles;
+  for (int i = lane; i < k; i += 32) {
+    const T v = (T)xe[i];
+    for (int r = 0; r < cs; ++r)
+      st_async_val(mapa_u32(cst_addr + (uint32_t)i * (uint32_t)sizeof(T), r), v, mapa_u32(req_bar_addr, r));
+  }
+  if (!fresh) return;
+  const uint32_t imm_addr = cst_addr + 8u * kSeatCstDoubles;
+  const uint32_t insn_addr = imm_addr + 8u * VSR_MAX_IMMS;
+  for (int i = lane; i < nm; i += 32) {
+    const double v = a.pt.imms[m0 + i];
+    for (int r = 0; r < cs; ++r) st_async_val(mapa_u32(imm_addr + 8u * i, r), v, mapa_u32(req_bar_addr, r));
+  }
+  for (int i = lane; i <= ni; i += 32) {
+    vsr_insn_t w = 0;  // pad word after END
+    if (i < ni) {
+      w = a.pt.insns[i0 + i];
+      const unsigned op = VSR_OP(w);
+      if (a.resident && op >= VSR_LOAD && op <= VSR_RPOW && op != VSR_PUSH && VSR_SRC(w) == VSR_SRC_VAR)
+        w = (w & ~((vsr_insn_t)0xffff << 16)) | ((vsr_insn_t)a.col_of_var[VSR_IDX(w)] << 16);
+      w = predecode(w);
+    }
+    for (int r = 0; r < cs; ++r) st_async_b64(mapa_u32(insn_addr + 8u * i, r), w, mapa_u32(req_bar_addr, r));
+  }
+}
+
+// One optimiser turn of seat `seat`, run by ONE warp of the leader CTA: take in the totals of the
+// sweep that served the seat's last request (if there was one), advance the run to its next
+// request, and when it finishes write its results and seat the next run of the launch's queue.
+// Ends by publishing the seat's next request.  Returns false when the seat is closed (queue
+// drained; the closing request has been sent).
 template <typename T, int K>
-__device__ __forceinline__ void seat_turn(const FitArgs& a, cooperative_groups::cluster_group& cluster, int seat,
-                                          int lane, int cs, FitState& S, double* ws, const double* cred,
-                                          SeatCtrl& ctrl, T* cst, SeatBook& book, int* s_drained) {
+__device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, FitState& S, double* ws,
+                                          const double* cred, SeatBook& book, int* s_drained, uint64_t* part_bar,
+                                          uint32_t ctrl_addr, uint32_t req_bar_addr) {
+  constexpr int W = fit_lanes<K>();
   const bool timing = a.phase_cycles != nullptr && lane == 0;
   long long ta = timing ? clock64() : 0;
-  int my_prog = ctrl.prog, my_k = ctrl.k;
+  int my_prog = book.prog, my_k = book.k;
   if (my_prog >= 0) {
     // component `lane` of (sum r^2, sum r df/dc_t) over the CTAs of the cluster in rank order;
     // lane 0 applies the penalty rule, lanes 1..k scale the gradient
@@ -457,16 +630,17 @@ __device__ __forceinline__ void seat_turn(const FitArgs& a, cooperative_groups::
       }
       if (__shfl_sync(0xffffffffu, late, 0)) bad = true;
     }
-    if (lane == 0) book.rf = bad ? a.O.penalty : f;
     if (lane >= 1 && lane <= K && lane - 1 < my_k) {
       const double gv = a.O.loss_scale * (2.0 * tot * inv_n);
-      S.rg[lane - 1] = (bad || !isfinite(gv)) ? 0.0 : gv;
+      ws[my_k + lane - 1] = (bad || !isfinite(gv)) ? 0.0 : gv;  // S.rg()
+    }
+    if (lane == 0) {
+      S.rf = bad ? a.O.penalty : f;
+      book.n_pass += 1;
     }
     __syncwarp();
-    S.rf = book.rf;
-    if (lane == 0) book.n_pass += 1;
   }
-  int fresh = 0;
+  bool fresh = false;
   for (;;) {
     if (my_prog < 0) {  // empty seat: take the next run of the launch
       int r = -1;
@@ -495,8 +669,8 @@ __device__ __forceinline__ void seat_turn(const FitArgs& a, cooperative_groups::
       }
       my_prog = prog;
       my_k = k;
-      fresh = 1;
-      fit_init(S, k, ws, a.x0 + (int64_t)slot * a.kstride);
+      fresh = true;
+      fit_init<W>(S, k, ws, a.x0 + (int64_t)slot * a.kstride);
       if (lane == 0) {
         book.slot = slot;
         book.t0 = 0ull;
@@ -504,17 +678,19 @@ __device__ __forceinline__ void seat_turn(const FitArgs& a, cooperative_groups::
       }
       __syncwarp();
     }
-    const int act = fit_step_call(S, a.O);
+    const int act = fit_step_call<W>(S, a.O);
+    __syncwarp();  // the state written back by the step is visible to every lane
     if (act == VSR_NEED_EVAL) break;
     // finished: results out, seat free, try to seat another run in this same turn
-    __syncwarp();
     if (lane == 0) {
       const int slot = book.slot;
       double* oc = a.out_consts + (int64_t)slot * a.kstride;
       double* ol = a.out_lastx + (int64_t)slot * a.kstride;
+      const double* xk = ws + 5 * my_k;
+      const double* lastx = ws + 4 * my_k;
       for (int i = 0; i < my_k; ++i) {
-        oc[i] = S.xk[i];
-        ol[i] = S.lastx[i];
+        oc[i] = xk[i];
+        ol[i] = lastx[i];
       }
       a.out_loss[slot] = S.old_fval;
       int32_t* info = a.out_info + (int64_t)slot * 4;
@@ -534,28 +710,18 @@ __device__ __forceinline__ void seat_turn(const FitArgs& a, cooperative_groups::
     }
     __syncwarp();
     my_prog = -1;
-    fresh = 0;
+    fresh = false;
   }
-  // Publish: the seat table entry and the trial constants go to EVERY CTA of the cluster as
-  // remote shared-memory stores (visible after the cluster barrier that ends the iteration), so
-  // that the sweepers never read remote memory on their critical path.  Nobody reads these
-  // locations during this iteration: the seat's bank is not the one being swept.
+  if (lane == 0) {
+    book.prog = my_prog;
+    book.k = my_k;
+    // the totals of the request that goes out now: cs CTAs x (K + 1) doubles
+    if (my_prog >= 0) mbar_expect_tx(part_bar, (uint32_t)cs * (uint32_t)(K + 1) * 8u);
+  }
   __syncwarp();
-  {
-    SeatCtrl v;
-    v.prog = my_prog;
-    v.k = my_k;
-    v.fresh = fresh;
-    v.drained = *s_drained;
-    for (int r = lane; r < cs; r += 32) *cluster.map_shared_rank(&ctrl, r) = v;
-    if (my_prog >= 0) {
-      for (int idx = lane; idx < cs * my_k; idx += 32) {
-        const int r = idx / my_k, i = idx - r * my_k;
-        cluster.map_shared_rank(cst, r)[i] = (T)S.xe[i];
-      }
-    }
-  }
+  publish_request<T>(a, cs, lane, my_prog, my_k, fresh, ws /* S.xe() */, ctrl_addr, req_bar_addr);
   if (timing && my_prog >= 0) book.t_logic += clock64() - ta;
+  return my_prog >= 0;
 }
 
 template <typename T, int K, int P>
@@ -563,10 +729,12 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) double smem[];
-  __shared__ SeatCtrl s_ctrl[kMaxSeats];
   __shared__ SeatBook s_book[kMaxSeats];
+  __shared__ __align__(8) uint64_t s_req_bar[kMaxSeats];   // request of seat g has arrived (every CTA)
+  __shared__ __align__(8) uint64_t s_part_bar[kMaxSeats];  // totals of seat g's request have arrived (leader)
+  __shared__ __align__(8) uint64_t s_bar;                  // TMA staging of the slice
+  __shared__ int s_ticket[kMaxSeats];                      // sweeper warps of this CTA that finished seat g's requests
   __shared__ int s_drained;
-  __shared__ __align__(8) uint64_t s_bar;
 
   const int cs = (int)cluster.num_blocks();
   const int crank = (int)cluster.block_rank();
@@ -575,20 +743,13 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   const int lane = tid & 31;
   const int warp = tid >> 5;
   const int G = a.seats;
-
   const int seat_d = a.seat_d;
-  const int wsd = a.off_cred - kFitStateDoubles;
 #define VSR_SEAT_STATE(g) (smem + (size_t)(g)*seat_d)
-#define VSR_SEAT_WS(g) (VSR_SEAT_STATE(g) + kFitStateDoubles)
-#define VSR_SEAT_CRED(g) (VSR_SEAT_STATE(g) + a.off_cred)
-#define VSR_SEAT_CST(g) (reinterpret_cast<T*>(VSR_SEAT_STATE(g) + a.off_cst))
-#define VSR_SEAT_IMM(g) (VSR_SEAT_STATE(g) + a.off_imm)
-#define VSR_SEAT_INSN(g) (reinterpret_cast<vsr_insn_t*>(VSR_SEAT_STATE(g) + a.off_insn))
 
   // ---- this CTA's slice of the points ----
-  // CTAs 1..cs-1 take `per` points each, the leader (rank 0) takes what is left at the end: in
-  // the two-bank schedule two of its warps are busy with optimiser steps during every sweep, and
-  // the host sizes `per` so that the leader's remainder fits its remaining warps.
+  // CTAs 1..cs-1 take `per` points each, the leader (rank 0) takes what is left at the end: its
+  // reserved warps never sweep, and the host sizes `per` so that the leader's remainder fits its
+  // remaining warps.
   const int64_t N = a.pts.n;
   const int64_t per = a.slice_stride;
   int64_t n0 = crank == 0 ? (int64_t)(cs - 1) * per : (int64_t)(crank - 1) * per;
@@ -599,26 +760,42 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   const T* X = static_cast<const T*>(a.pts.X);
   const T* y = static_cast<const T*>(a.pts.y);
 
+  double* wpart = smem + (size_t)G * seat_d;                      // [G][nw][K+1]
+  double* scratch = wpart + (size_t)G * nw * (K + 1);             // [(K+1)][threads]
   T* xs = nullptr;
   T* ys = nullptr;
   const int stride = a.slice_stride;
+  if (tid == 0) {
+    for (int g = 0; g < kMaxSeats; ++g) {
+      mbar_init(&s_req_bar[g], 1);
+      mbar_init(&s_part_bar[g], 1);
+      s_ticket[g] = 0;
+    }
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    s_drained = 0;
+  }
+  if (tid < kMaxSeats) {
+    s_book[tid].prog = -1;
+    s_book[tid].k = 0;
+    s_book[tid].t0 = 0ull;
+    s_book[tid].t_logic = s_book[tid].t_seated = s_book[tid].n_pass = 0;
+  }
+  __syncthreads();
   if (a.resident) {
-    ys = reinterpret_cast<T*>(smem + (size_t)G * seat_d + (size_t)(K + 1) * blockDim.x);
+    ys = reinterpret_cast<T*>(scratch + (size_t)(K + 1) * blockDim.x);
     xs = ys + stride;
     constexpr int kAlign = 16 / (int)sizeof(T);
     const int full = cnt & ~(kAlign - 1);  // elements per column that move as 16-byte units
     const bool use_tma = a.tma_ok && full > 0;
     if (tid == 0 && use_tma) {
       const uint32_t bytes = (uint32_t)full * (uint32_t)sizeof(T);
-      mbar_init(&s_bar, 1);
-      mbar_fence_init();
       mbar_expect_tx(&s_bar, bytes * (uint32_t)(a.n_cols + 1));
       tma_bulk_load(ys, y + n0, bytes, &s_bar);
       for (int j = 0; j < VSR_MAX_VARS; ++j)
         if (a.col_of_var[j] >= 0)
           tma_bulk_load(xs + (size_t)a.col_of_var[j] * stride, X + (int64_t)j * a.pts.ldx + n0, bytes, &s_bar);
     }
-    __syncthreads();  // the armed barrier is visible
     {
       // everything TMA does not move (all of it when the caller's memory is unaligned): coalesced loads
       const int first = use_tma ? full : 0;
@@ -631,123 +808,113 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
       }
     }
     if (use_tma) mbar_wait(&s_bar, 0);  // every thread observes the completed transaction
+    __syncthreads();                    // ... and the plain stores of the others
   }
-  if (tid < kMaxSeats) {
-    s_ctrl[tid].prog = -1;
-    s_ctrl[tid].k = 0;
-    s_ctrl[tid].fresh = 0;
-    s_ctrl[tid].drained = tid < G ? 0 : 1;
-    s_book[tid].t0 = 0ull;
-    s_book[tid].t_logic = s_book[tid].t_seated = s_book[tid].n_pass = 0;
-  }
-  if (tid == 0) s_drained = 0;
-  __syncthreads();
 
-  // every CTA of the cluster is running (and has its seat table initialised) before any DSMEM access
+  // every CTA of the cluster is running and has initialised its barriers before any DSMEM access
   cluster.sync();
-  double* r_smem = cluster.map_shared_rank(smem, 0);
 
-  // ---- the schedule ----
-  // Seats are split in banks (seat g -> bank g & 1; one bank when the cluster is too small to
-  // spare warps).  Iteration t SWEEPS the requests of bank t & 1, while the optimisers of the
-  // OTHER bank take in their previous sweep's totals and advance their runs to the next
-  // request.  One cluster barrier per iteration; a run advances one pass every two iterations,
-  // and with two banks the optimiser turns (16-21 k cycles of one warp each) are hidden behind
-  // the other bank's sweeps.
-  //
-  // Who does what in the leader CTA: when the slice layout reserves warps (a.reserved = 2, see
-  // choose_geometry) warps 0..1 NEVER sweep and run the optimiser turns (two banks: warp j takes
-  // seat lb + 2 j; one bank: warp j takes seats j, j + 2, ...), and the leader's slice is always
-  // swept by warps 2..nw-1, so the partition of the points over threads -- and with it the
-  // rounding of every sum -- does not depend on the number of seats or banks.  Without reserved
-  // warps (small clusters, one bank) warp g takes seat g and every warp sweeps.
-  const int n_banks = a.banks;  // 1 or 2
+  // ---- roles ----
+  // Optimiser warps: the LAST n_opt warps of the leader CTA (the warp scheduler prefers higher warp
+  // ids, and a turn is the latency-critical part of a pass); optimiser warp j serves seats j,
+  // j + n_opt, ...  With reserved warps (a.reserved > 0, see choose_geometry) they never sweep and
+  // the leader's slice is sized for the remaining warps; without (small CTAs) they sweep as well.
   const int reserved = crank == 0 ? a.reserved : 0;
-  const bool may_logic = crank == 0 && (reserved > 0 ? warp < reserved : warp < G);
-  const bool sweeper = warp >= reserved;
-  const int swarp = warp - reserved, nsw = nw - reserved;
-  int stid = swarp * 32 + lane, snt = nsw * 32;
+  const int n_opt = a.reserved > 0 ? a.reserved : (G < nw ? G : nw);
+  const bool is_opt = crank == 0 && warp >= nw - n_opt;
+  const bool sweeper = warp < nw - reserved;
+  const int nsw = nw - reserved;  // sweeper warps of this CTA
+  int stid = warp * 32 + lane, snt = nsw * 32;
   keep_in_register(stid);
   keep_in_register(snt);
-  bool prev_empty = false;
-  for (int t = 0;; ++t) {
-    const int sb = t & 1;   // bank swept now
-    const int lb = sb ^ 1;  // bank whose optimisers run now
-    if (may_logic && (n_banks == 2 || lb == 0)) {
-      // seats of bank lb this warp serves
-      const int first = reserved > 0 ? (n_banks == 2 ? lb + 2 * warp : warp) : warp;
-      const int step = reserved > 0 ? (n_banks == 2 ? 2 * reserved : reserved) : G;
-      for (int g = first; g < G; g += step) {
-        if (n_banks == 2 && (g & 1) != lb) continue;
-        seat_turn<T, K>(a, cluster, g, lane, cs, *reinterpret_cast<FitState*>(VSR_SEAT_STATE(g)), VSR_SEAT_WS(g),
-                        VSR_SEAT_CRED(g), s_ctrl[g], VSR_SEAT_CST(g), s_book[g], &s_drained);
-      }
-    }
 
-    // ---- bank sb: seat table (this CTA's copy, published one iteration ago, stable now) ----
-    int active = 0;
-    bool empty = true;
-    for (int g = n_banks == 2 ? sb : 0; g < G; g += n_banks) {
-      if (n_banks == 1 && sb == 1) break;  // single bank: odd iterations only run the optimisers
-      const SeatCtrl c = s_ctrl[g];
-      if (c.prog >= 0) active |= 1 << g;
-      if (c.prog >= 0 || !c.drained) empty = false;
-    }
+  uint32_t req_phase = 0, live = sweeper ? ((1u << G) - 1u) : 0u;
+  uint32_t part_phase = 0, opt_wait = 0, opt_live = 0;
+  if (is_opt)
+    for (int g = warp - (nw - n_opt); g < G; g += n_opt) opt_live |= 1u << g;
+  const uint32_t ctrl0 = smem_u32(smem) + 8u * (uint32_t)a.off_ctrl;
 
-    if (sweeper && active) {
+  while (live | opt_live) {
+    bool progress = false;
+    // ---- optimiser turns of my seats whose totals have arrived ----
+    if (opt_live) {
+      const bool only = !live && (opt_live & (opt_live - 1)) == 0;  // nothing else to do: block
       for (int g = 0; g < G; ++g) {
-        if (!((active >> g) & 1)) continue;
-        const SeatCtrl c = s_ctrl[g];
-        if (c.fresh) {
-          // the run was seated one iteration ago: its program into this CTA's seat area, VAR
-          // operands rewritten to slice columns, handler ids over the opcode bytes
-          const int i0 = a.pt.insn_off[c.prog], ni = a.pt.insn_off[c.prog + 1] - i0;
-          const int m0 = a.pt.imm_off[c.prog], nm = a.pt.imm_off[c.prog + 1] - m0;
-          vsr_insn_t* s_insn = VSR_SEAT_INSN(g);
-          double* s_imm = VSR_SEAT_IMM(g);
-          for (int i = stid; i < ni; i += snt) {
-            vsr_insn_t w = a.pt.insns[i0 + i];
-            const unsigned op = VSR_OP(w);
-            if (a.resident && op >= VSR_LOAD && op <= VSR_RPOW && op != VSR_PUSH && VSR_SRC(w) == VSR_SRC_VAR)
-              w = (w & ~((vsr_insn_t)0xffff << 16)) | ((vsr_insn_t)a.col_of_var[VSR_IDX(w)] << 16);
-            s_insn[i] = predecode(w);
-          }
-          if (stid == 0) s_insn[ni] = 0;  // pad word after END
-          for (int i = stid; i < nm; i += snt) s_imm[i] = a.pt.imms[m0 + i];
+        if (!((opt_live >> g) & 1u)) continue;
+        if ((opt_wait >> g) & 1u) {
+          const uint32_t par = (part_phase >> g) & 1u;
+          if (only)
+            mbar_wait(&s_part_bar[g], par);
+          else if (!mbar_test(&s_part_bar[g], par))
+            continue;
+          part_phase ^= 1u << g;
         }
+        double* seat = VSR_SEAT_STATE(g);
+        const bool open = seat_turn<T, K>(a, lane, cs, *reinterpret_cast<FitState*>(seat), seat + kFitStateDoubles,
+                                          seat + a.off_cred, s_book[g], &s_drained, &s_part_bar[g],
+                                          ctrl0 + 8u * (uint32_t)(g * seat_d), smem_u32(&s_req_bar[g]));
+        if (open)
+          opt_wait |= 1u << g;
+        else
+          opt_live &= ~(1u << g);
+        progress = true;
       }
-      sweep_barrier(snt);
+    }
+    // ---- sweeps of the seats whose request has arrived ----
+    if (live) {
+      const bool only = !opt_live && (live & (live - 1)) == 0;
       for (int g = 0; g < G; ++g) {
-        if (!((active >> g) & 1)) continue;
+        if (!((live >> g) & 1u)) continue;
+        const uint32_t par = (req_phase >> g) & 1u;
+        if (only)
+          mbar_wait(&s_req_bar[g], par);
+        else if (!mbar_test(&s_req_bar[g], par))
+          continue;
+        req_phase ^= 1u << g;
+        progress = true;
         // the seat's code area through ONE opaque byte offset: without the asm the compiler
-        // re-derives the three pointers from (g, blockDim, kmax, ...) for every bytecode
-        // instruction -- 17 of the 36 instructions of the dispatch sequence -- instead of
-        // spending registers on them
-        unsigned code_off = (unsigned)(reinterpret_cast<char*>(VSR_SEAT_INSN(g)) - reinterpret_cast<char*>(smem));
+        // re-derives the pointers from (g, seat_d, ...) for every bytecode instruction instead
+        // of spending registers on them
+        unsigned code_off = (unsigned)((g * seat_d + a.off_insn) * 8);
         asm volatile("" : "+r"(code_off));
         const vsr_insn_t* c_insn = reinterpret_cast<const vsr_insn_t*>(reinterpret_cast<char*>(smem) + code_off);
         const double* c_imm = reinterpret_cast<const double*>(c_insn) - VSR_MAX_IMMS;
         const T* c_cst = reinterpret_cast<const T*>(c_imm - kSeatCstDoubles);
-        double* scratch = smem + (size_t)G * seat_d;
+        const SeatCtrl c = *reinterpret_cast<const SeatCtrl*>(c_imm - kSeatCstDoubles - kSeatCtrlDoubles);
+        if (c.prog < 0) {  // the seat is closed
+          live &= ~(1u << g);
+          continue;
+        }
         if (a.resident)
           sweep_slice<T, K, P>(c_insn, c_imm, c_cst, xs, ys, stride, cnt, scratch, stid, snt);
         else
           sweep_points<T, K, P>(c_insn, c_imm, c_cst, X, y, a.pts.ldx, n0, n1, scratch, stid, snt);
-        block_totals<K>(scratch, stid, snt,
-                        r_smem + (size_t)g * seat_d + kFitStateDoubles + wsd + crank * (K + 1));
+        double* mine = wpart + ((size_t)g * nw + warp) * (K + 1);
+        warp_totals<K>(scratch, stid, snt, lane, mine);
+        __syncwarp();
+        int t = 0;
+        if (lane == 0) {
+          __threadfence_block();
+          t = atomicAdd(&s_ticket[g], 1);
+        }
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if ((t + 1) % nsw == 0) {
+          // last warp of this CTA for this request: the CTA's sums in warp order, to the leader
+          __threadfence_block();
+          if (lane <= K) {
+            const double* col = wpart + (size_t)g * nw * (K + 1) + lane;
+            double acc = 0.0;
+            for (int w = 0; w < nsw; ++w) acc += col[w * (K + 1)];
+            const uint32_t dst = smem_u32(VSR_SEAT_STATE(g) + a.off_cred + crank * (K + 1) + lane);
+            st_async_val(mapa_u32(dst, 0), acc, mapa_u32(smem_u32(&s_part_bar[g]), 0));
+          }
+        }
       }
     }
-    cluster.sync();  // requests of bank lb and partial sums of bank sb are visible
-    if (empty && prev_empty) break;  // both banks empty, queue drained: uniform over the cluster
-    prev_empty = empty;
+    if (!progress) __nanosleep(40);
   }
 #undef VSR_SEAT_STATE
-#undef VSR_SEAT_WS
-#undef VSR_SEAT_CRED
-#undef VSR_SEAT_CST
-#undef VSR_SEAT_IMM
-#undef VSR_SEAT_INSN
-  // no CTA may exit while another can still read its shared memory
+  // no CTA may exit while another can still write to (or wait on) its shared memory
   cluster.sync();
 }
 
@@ -760,7 +927,6 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalArgs a) {
   if (pair >= a.n_pairs) return;
   const int prog = a.pair_prog[pair];
   const int k = a.pt.k[prog];
-  const int nw = (blockDim.x + 31) >> 5;
   double* red = smem;  // reduction scratch of block_totals: [(K+1)][blockDim.x]
   const int n_red = (K + 1) * (int)blockDim.x;
   T* cst = reinterpret_cast<T*>(red + n_red);

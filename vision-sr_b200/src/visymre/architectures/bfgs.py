@@ -214,7 +214,8 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
     # ---- Q7 normalisation ----
     norm = _opt(cfg, "normalization_type")
     if norm == "NMSE":
-        mean_y = float(yt_fit.double().mean())
+        # mean of the FULL y in y's own dtype, rows dropped by idx_remove included (bfgs.py:86-90)
+        mean_y = float(np.mean(yt.detach().cpu().numpy()))
         scale = 1.0 / mean_y if abs(mean_y) > 1e-06 else 1.0
     elif norm == "MSE":
         scale = 1.0
@@ -312,10 +313,13 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
             vals[j["rest"]] = j["x"]
             pruned_loss = j["loss"]
         else:  # every constant pruned: evaluate the constant-free expression
-            zprog = compile_sympy(c.prog.expr.subs({s: 0.0 for s in csyms}), 0, variables)
-            eng.set_programs([zprog])
-            zl, _ = eng.eval([0], torch.zeros((1, 1)), dtype=score_dtype)
-            pruned_loss = float(zl.cpu().numpy()[0])
+            try:
+                zprog = compile_sympy(c.prog.expr.subs({s: 0.0 for s in csyms}), 0, variables)
+                eng.set_programs([zprog])
+                zl, _ = eng.eval([0], torch.zeros((1, 1)), dtype=score_dtype)
+                pruned_loss = float(zl.cpu().numpy()[0])
+            except Exception:  # noqa: BLE001 -- a singular tree (zoo*x_1 ...): bfgs.py:196-202 scores it 1e9,
+                pruned_loss = 1e9  # the prune is rejected and the unpruned fit stays
         if score_dtype == fitter.F32:
             pruned_loss = np.float32(pruned_loss)
         if rows_removed:

@@ -91,6 +91,13 @@ class Engine:
     def set_profiling(self, on):
         self._check(self.lib.vsr_set_profiling(self._h, int(bool(on))))
 
+    def set_geometry(self, spec=None):
+        """Measurement hook: "cluster:threads:seats[:optimiser warps]" overrides the launch geometry
+        of ``fit`` (0 or a missing item keeps the built-in choice); None or "" restores it."""
+        v = [int(x) for x in str(spec).split(":")] if spec else []
+        v = (v + [0, 0, 0, 0])[:4]
+        self._check(self.lib.vsr_set_geometry(self._h, *v))
+
     def set_phase_buffer(self, tensor):
         """int64 device tensor [n_slots, 8] (or None) for per-run phase cycle counts."""
         self._phase = tensor

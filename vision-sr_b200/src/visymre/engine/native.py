@@ -76,6 +76,7 @@ SIGNATURES = {
     "vsr_set_profiling": (ctypes.c_int, [vp, ctypes.c_int32]),
     "vsr_read_profile": (ctypes.c_int, [vp, c_f64p]),
     "vsr_set_phase_buffer": (ctypes.c_int, [vp, vp]),
+    "vsr_set_geometry": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
 }
 
 _lib = None

@@ -82,6 +82,17 @@ def allgather_best(rec, group=None):
     return merge_records(torch.stack(parts))
 
 
+def empty_result(n_slots, kstride, device):
+    """What a rank that holds no run reports: every slot nan / not run."""
+    from .fitter import FitResult
+    nan = float("nan")
+    return FitResult(consts=torch.full((n_slots, kstride), nan, dtype=torch.float64, device=device),
+                     lastx=torch.full((n_slots, kstride), nan, dtype=torch.float64, device=device),
+                     loss=torch.full((n_slots,), nan, dtype=torch.float64, device=device),
+                     final_mse=torch.full((n_slots,), nan, dtype=torch.float64, device=device),
+                     info=torch.full((n_slots, 4), -1, dtype=torch.int32, device=device))
+
+
 def fit_sharded(engine, programs_k, n_restarts, x0, opts, cost=None, group=None):
     """Fit a beam with its runs sharded over the ranks of ``group``.
 
@@ -98,7 +109,12 @@ def fit_sharded(engine, programs_k, n_restarts, x0, opts, cost=None, group=None)
         cost = np.repeat(np.asarray(programs_k, dtype=np.float64) + 1.0, R)
     mine_idx = partition_runs(cost, world)[rank]
     run_prog = (mine_idx // R).astype(np.int32)
-    res = engine.fit(run_prog, mine_idx.astype(np.int32), x0, opts)
+    if len(mine_idx):
+        res = engine.fit(run_prog, mine_idx.astype(np.int32), x0, opts)
+    else:
+        # more ranks than runs: this rank fits nothing but must still take part in the all-gather
+        # (vsr_fit rejects an empty run list; raising here would leave the others in the collective)
+        res = empty_result(C * R, int(torch.as_tensor(x0).shape[1]), engine.device)
     mine = torch.zeros(C * R, dtype=torch.bool, device=res.loss.device)
     mine[torch.as_tensor(mine_idx, device=mine.device)] = True
     rec = local_best_records(res.final_mse, res.loss, res.lastx, C, R, mine)
