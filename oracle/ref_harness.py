@@ -8,6 +8,7 @@ absent here -- none of which ``bfgs()`` touches -- are replaced by inert stubs
 ``sys.path``: both trees use the top-level package name ``src``.
 """
 import importlib
+import os
 import pickle
 import sys
 import types
@@ -51,15 +52,36 @@ def _install_stubs():
         sys.modules[name] = _StubModule(name)
 
 
-def load(ref_root=REF_ROOT):
+VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py
+
+
+def available():
+    """Where the unmodified reference can be imported from: its tree (build container) or the
+    byte-compiled copy oracle/build_ref.py made (GPU box); None when neither is here."""
+    if os.path.isdir(os.path.join(REF_ROOT, "src", "visymre")):
+        return REF_ROOT
+    tag = os.path.join(VENDORED, "PYTHON")
+    if os.path.exists(tag) and open(tag).read().strip() == f"{sys.version_info.major}.{sys.version_info.minor}":
+        return VENDORED
+    return None
+
+
+def load(ref_root=None):
     """Returns (bfgs_module, model_module_or_None, test_data)."""
+    ref_root = ref_root or available()
+    if ref_root is None:
+        raise ImportError("neither /root/reference nor oracle/_ref (python oracle/build_ref.py) is here")
     _install_stubs()
     if ref_root not in sys.path:
         sys.path.insert(0, ref_root)
     ref_bfgs = importlib.import_module("src.visymre.architectures.bfgs")
     importlib.import_module("src.visymre.dclasses")
-    raw = open(f"{ref_root}/scripts/weights/meta/metadata.h5", "rb").read()
-    test_data = pickle.loads(raw[2048:2048 + 2926])
+    vendored = os.path.join(ref_root, "metadata.pkl")
+    if os.path.exists(vendored):
+        test_data = pickle.loads(open(vendored, "rb").read())
+    else:
+        raw = open(f"{ref_root}/scripts/weights/meta/metadata.h5", "rb").read()
+        test_data = pickle.loads(raw[2048:2048 + 2926])
     test_data.id2word[3] = "constant"  # what fitfunc2 does before fitting (model.py:452)
     try:
         ref_model = importlib.import_module("src.visymre.architectures.model")

@@ -105,6 +105,7 @@ struct vsr_handle {
   PinnedBuf h_lists;
   int64_t launches = 0;
   int hook[4] = {0, 0, 0, 0};  // VSR_GEOMETRY measurement hook, read once in vsr_create
+  int steal_span = 3;          // a launch takes runs of groups up to this many tangent widths narrower
   // measurement hooks
   bool profiling = false;
   long long* phase_cycles = nullptr;  // optional device buffer [n_slots][8], see vsr_set_phase_buffer
@@ -253,19 +254,24 @@ Geometry choose_geometry(int64_t N, int P, int cap_threads, int forced_warps, in
     threads += 32 * res;
     nw = threads / 32;
     g.reserved = res;
-  } else if (res > 0 && nw > res) {
-    const int64_t denom = (int64_t)(cs - 1) * nw + (nw - res);
-    int64_t per2 = (N * nw + denom - 1) / denom;
-    per2 = (per2 + 31) & ~(int64_t)31;
-    const int64_t lead = N - (int64_t)(cs - 1) * per2;
-    // accept only if nobody needs more tile iterations than with equal slices
-    const int64_t tile = (int64_t)threads * P, tile_lead = (int64_t)(nw - res) * 32 * P;
-    const int64_t it0 = (per + tile - 1) / tile;
-    const int64_t it_others = (per2 + tile - 1) / tile;
-    const int64_t it_lead = lead > 0 ? (lead + tile_lead - 1) / tile_lead : 0;
-    if (it_others <= it0 && it_lead <= it0 && lead <= per2 && (cs == 1 || lead >= 0)) {
-      per = per2;
-      g.reserved = res;
+  } else {
+    // as many of the wanted warps as the points leave room for (N = 10 000 on 8 x 640 threads x 2
+    // points leaves 240 point slots: three warps)
+    for (; res > 0 && g.reserved == 0; --res) {
+      if (nw <= res) continue;
+      const int64_t denom = (int64_t)(cs - 1) * nw + (nw - res);
+      int64_t per2 = (N * nw + denom - 1) / denom;
+      per2 = (per2 + 31) & ~(int64_t)31;
+      const int64_t lead = N - (int64_t)(cs - 1) * per2;
+      // accept only if nobody needs more tile iterations than with equal slices
+      const int64_t tile = (int64_t)threads * P, tile_lead = (int64_t)(nw - res) * 32 * P;
+      const int64_t it0 = (per + tile - 1) / tile;
+      const int64_t it_others = (per2 + tile - 1) / tile;
+      const int64_t it_lead = lead > 0 ? (lead + tile_lead - 1) / tile_lead : 0;
+      if (it_others <= it0 && it_lead <= it0 && lead <= per2 && lead >= 0) {
+        per = per2;
+        g.reserved = res;
+      }
     }
   }
   g.threads = threads;
@@ -412,6 +418,7 @@ int vsr_create(int device, vsr_handle** out) {
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   if (const char* env = getenv("VSR_GEOMETRY")) sscanf(env, "%d:%d:%d:%d", &h->hook[0], &h->hook[1], &h->hook[2], &h->hook[3]);
+  if (const char* env = getenv("VSR_STEAL_SPAN")) h->steal_span = atoi(env);
   // scratch every fit needs, allocated here rather than inside the first fit: run lists (pinned
   // + device), run counters, eval partials, the side streams and their events
   e = h->h_lists.reserve(256 << 10);
@@ -806,13 +813,23 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     g.prog.swap(p2);
     g.slot.swap(s2);
   }
-  // lists: per group prog | slot ; then for the final score: prog | slot | slot
+  // lists: programs of all groups (launch order) | their slots ; then for the final score: prog | slot
   std::vector<int32_t> all;
-  std::vector<size_t> off;
+  std::vector<int32_t> g_begin;  // first run of each group in the global lists
   for (auto& g : groups) {
-    off.push_back(all.size());
+    g_begin.push_back((int32_t)all.size());
     all.insert(all.end(), g.prog.begin(), g.prog.end());
-    all.insert(all.end(), g.slot.begin(), g.slot.end());
+  }
+  g_begin.push_back((int32_t)all.size());
+  const size_t n_listed = all.size();
+  for (auto& g : groups) all.insert(all.end(), g.slot.begin(), g.slot.end());
+  // what any launch may meet when it takes runs of a narrower group: the longest program, and the
+  // union of the variables (a resident slice stages the columns of that union)
+  int all_insn = 0;
+  unsigned all_vars = 0;
+  for (auto& g : groups) {
+    all_insn = std::max(all_insn, g.max_insn);
+    all_vars |= g.var_mask;
   }
   const size_t score_off = all.size();
   int s_kmax = 0, s_insn = 0, s_imm = 0;
@@ -865,9 +882,20 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     vsr::FitArgs a;
     a.pt = table_of(h);
     a.pts = points_of(ps);
-    a.run_prog = dl + off[gi];
-    a.run_slot = dl + off[gi] + n;
-    a.n_runs = n;
+    a.run_prog = dl;
+    a.run_slot = dl + n_listed;
+    // queues: the group's own, then the next narrower groups of the same gradient mode, as long as
+    // their kernels are at most `steal_span` widths apart (a k-run costs a K-wide kernel's sweep)
+    a.n_queues = 0;
+    for (size_t gj = gi; gj < groups.size() && a.n_queues < vsr::kMaxQueues; ++gj) {
+      if (gj > gi && (groups[gj].grad_mode != g.grad_mode || groups[gj].K == 0 || g.K - groups[gj].K > h->steal_span ||
+                      gj != gi + (size_t)a.n_queues))
+        break;
+      a.q_begin[a.n_queues] = g_begin[gj];
+      a.q_end[a.n_queues] = g_begin[gj + 1];
+      ++a.n_queues;
+    }
+    for (int q = a.n_queues; q < vsr::kMaxQueues; ++q) a.q_begin[q] = a.q_end[q] = 0;
     a.kstride = kstride;
     a.x0 = x0;
     a.out_consts = out_consts;
@@ -889,7 +917,8 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     if (hook_threads > 0) cap = std::min(cap, std::max(32, hook_threads & ~31));
     const int max_cluster = hook_cluster > 0 ? std::min(hook_cluster, kMaxCluster) : kMaxCluster;
     int n_cols = 0;
-    for (int j = 0; j < VSR_MAX_VARS; ++j) a.col_of_var[j] = ((g.var_mask >> j) & 1u) ? n_cols++ : -1;
+    for (int j = 0; j < VSR_MAX_VARS; ++j) a.col_of_var[j] = ((all_vars >> j) & 1u) ? n_cols++ : -1;
+    g.max_insn = all_insn;
     Geometry geo = choose_geometry(g.kmax == 0 ? 1 : ps.n, P, cap, opts->warps_per_run, g.kmax, g.K, g.max_insn,
                                    n_cols, elem, max_cluster, hook_seats > 0 ? hook_seats : kDefaultSeats,
                                    hook_reserved);

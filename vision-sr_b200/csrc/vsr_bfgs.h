@@ -121,7 +121,13 @@ struct LanesT {
 #define VSR_UNROLL4
 #define VSR_FI inline
 #endif
+#if defined(__CUDA_ARCH__)
+// k <= W on the device: at most ONE trip, spelled so that the compiler sees it (as a counted loop
+// it unrolled every O(k) statement four times with a remainder loop)
+#define VSR_FOR_K(i, k) for (int i = LN::first(); i < (k); i = (k))
+#else
 #define VSR_FOR_K(i, k) for (int i = LN::first(); i < (k); i += LN::step())
+#endif
 
 // DCSRCH task codes
 enum { DC_START = 0, DC_FG = 1, DC_CONV = 2, DC_WARN = 3, DC_ERROR = 4 };
@@ -434,8 +440,7 @@ VSR_HDN VSR_FI bool quadmin(double a, double fa, double fpa, double b, double fb
 #define VSR_CO_YIELD_(S, n)   \
   do {                        \
     (S).pc = (n) + 1;         \
-    G_ = (S);                 \
-    return VSR_NEED_EVAL;     \
+    goto vsr_yield_;          \
     case (n) + 1:;            \
   } while (0)
 #define VSR_CO_YIELD(S) VSR_CO_YIELD_(S, __COUNTER__)
@@ -536,9 +541,16 @@ template <int W = 32>
 VSR_HDN VSR_FI int fit_step(FitState& G_, const FitOpts& O) {
   using namespace detail;
   using LN = LanesT<W>;
+#if defined(__CUDA_ARCH__)
+  // the state and the workspace live in shared memory: LDS/STS instead of generic loads and stores
+  __builtin_assume(__isShared(&G_));
+#endif
   FitState S = G_;  // private copy: registers (and an L1-resident stack) for the length of the turn
   const int k = S.k;
   double* const v_xe = S.ws;
+#if defined(__CUDA_ARCH__)
+  __builtin_assume(__isShared(v_xe));
+#endif
   double* const v_rg = S.ws + k;
   double* const v_cx = S.ws + 2 * k;
   double* const v_cg = S.ws + 3 * k;
@@ -868,6 +880,9 @@ VSR_HDN VSR_FI int fit_step(FitState& G_, const FitOpts& O) {
     default:
       return VSR_DONE;
   }
+vsr_yield_:  // the one exit of every VSR_CO_YIELD: the private copy goes back to shared memory
+  G_ = S;
+  return VSR_NEED_EVAL;
 }
 
 }  // namespace vsr

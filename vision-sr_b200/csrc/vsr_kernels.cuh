@@ -45,13 +45,20 @@ struct Points {
 };
 
 constexpr int kMaxSeats = 8;  // runs a cluster can work on at a time
+constexpr int kMaxQueues = 4;  // run queues a launch pulls from: its own and up to three narrower groups'
 
 struct FitArgs {
   ProgramTable pt;
   Points pts;
-  const int32_t* run_prog;  // [n_runs] (this launch's group), in queue order
-  const int32_t* run_slot;  // [n_runs]
-  int32_t n_runs;
+  // Runs of ALL width groups of the vsr_fit call, group after group in launch order (widest
+  // first).  The clusters of this launch pull from queue[0] (their own group) until it is drained,
+  // then from the queues of the next narrower groups: a K-wide kernel evaluates any k <= K, and a
+  // seat that would otherwise stay empty behind a long run takes work the narrower launches are
+  // still waiting for SMs to start on.
+  const int32_t* run_prog;  // [all runs]
+  const int32_t* run_slot;  // [all runs]
+  int32_t n_queues;         // queues this launch may pull from (own group first), <= kMaxQueues
+  int32_t q_begin[kMaxQueues], q_end[kMaxQueues];  // their ranges in run_prog / run_slot
   int32_t kstride;
   const double* x0;
   double* out_consts;
@@ -70,9 +77,11 @@ struct FitArgs {
   int32_t kmax, max_insn, max_imm;  // maxima over this launch's programs (size the seat areas)
   int32_t n_cols;                   // columns of X this launch's programs read
   int32_t col_of_var[VSR_MAX_VARS]; // slice column of variable j (-1: unused)
-  int32_t* queue;           // [1] index of the next run to hand out (zeroed by the host)
-  long long* phase_cycles;  // optional [n_slots][8]: cycles of the run's optimiser lane 0:
-                            // [0] optimiser turns, [3] everything else while seated, [7] passes
+  int32_t* queue;           // [n_queues] next run of each queue, relative to q_begin (zeroed by the host)
+  long long* phase_cycles;  // optional [n_slots][8]: cycles of the run's optimiser lane 0: [0] optimiser turns
+                            // ([1] taking in the totals, [2] the BFGS step, [4] publishing the request),
+                            // [3] everything else while seated, [5] / [6] %globaltimer when the run was seated /
+                            // finished, [7] passes
   FitOpts O;
 };
 
@@ -535,7 +544,8 @@ static __device__ __noinline__ int fit_step_call(FitState& S, const FitOpts& O) 
 struct SeatCtrl {
   int prog;  // program of the seated run, -1: the seat is closed (queue drained)
   int k;     // its number of constants
-  int n_insn, pad;
+  int n_insn;
+  int age;   // passes the run has behind it: the sweepers serve the oldest ready request first
 };
 
 // what the optimiser warp of a seat carries from one turn to the next (leader CTA only)
@@ -546,13 +556,13 @@ struct SeatBook {
   int pad;
   unsigned long long t0;  // TimedFun clock (bfgs.py:29-33)
   double rf;              // scratch: lane 0 -> all lanes
-  long long t_logic, t_seated, n_pass;  // phase_cycles bookkeeping
+  long long t_logic, t_seated, n_pass, t_take, t_step, t_pub, ns_seated;  // phase_cycles bookkeeping
 };
 
 // Sends the request of seat `seat` to every CTA of the cluster.  `fresh`: the program goes along
 // (predecoded, VAR operands rewritten to slice columns when the slices are resident).
 template <typename T>
-__device__ __forceinline__ void publish_request(const FitArgs& a, int cs, int lane, int prog, int k, bool fresh,
+__device__ __forceinline__ void publish_request(const FitArgs& a, int cs, int lane, int prog, int k, bool fresh, int age,
                                                 const double* xe, uint32_t ctrl_addr, uint32_t req_bar_addr) {
   int i0 = 0, ni = 0, m0 = 0, nm = 0;
   if (prog >= 0 && fresh) {
@@ -564,19 +574,25 @@ __device__ __forceinline__ void publish_request(const FitArgs& a, int cs, int la
   const uint32_t bytes = 16u + (prog >= 0 ? (uint32_t)k * (uint32_t)sizeof(T) : 0u) +
                          (fresh && prog >= 0 ? (uint32_t)(nm + ni + 1) * 8u : 0u);
   for (int r = lane; r < cs; r += 32) mbar_expect_tx_cluster(mapa_u32(req_bar_addr, r), bytes);
-  // header
-  if (lane < 2) {
-    const uint64_t w = lane == 0 ? ((uint64_t)(uint32_t)prog | ((uint64_t)(uint32_t)k << 32)) : (uint64_t)(uint32_t)ni;
-    for (int r = 0; r < cs; ++r) st_async_b64(mapa_u32(ctrl_addr + 8u * lane, r), w, mapa_u32(req_bar_addr, r));
+  // header words and trial constants (in the sweep's arithmetic type): one (CTA, item) pair per lane;
+  // cs is a power of two
+  const uint32_t cst_addr = ctrl_addr + 8u * kSeatCtrlDoubles;
+  {
+    const int n_items = 2 + (prog >= 0 ? k : 0);
+    const int sh = __ffs(cs) - 1;
+    for (int idx = lane; idx < (n_items << sh); idx += 32) {
+      const int r = idx & (cs - 1), it = idx >> sh;
+      const uint32_t bar = mapa_u32(req_bar_addr, r);
+      if (it < 2) {
+        const uint64_t w = it == 0 ? ((uint64_t)(uint32_t)prog | ((uint64_t)(uint32_t)k << 32))
+                                   : ((uint64_t)(uint32_t)ni | ((uint64_t)(uint32_t)age << 32));
+        st_async_b64(mapa_u32(ctrl_addr + 8u * it, r), w, bar);
+      } else {
+        st_async_val(mapa_u32(cst_addr + (uint32_t)(it - 2) * (uint32_t)sizeof(T), r), (T)xe[it - 2], bar);
+      }
+    }
   }
   if (prog < 0) return;
-  // trial constants in the sweep's arithmetic type
-  const uint32_t cst_addr = ctrl_addr + 8u * kSeatCtrlDoubles;
-  for (int i = lane; i < k; i += 32) {
-    const T v = (T)xe[i];
-    for (int r = 0; r < cs; ++r)
-      st_async_val(mapa_u32(cst_addr + (uint32_t)i * (uint32_t)sizeof(T), r), v, mapa_u32(req_bar_addr, r));
-  }
   if (!fresh) return;
   const uint32_t imm_addr = cst_addr + 8u * kSeatCstDoubles;
   const uint32_t insn_addr = imm_addr + 8u * VSR_MAX_IMMS;
@@ -604,7 +620,7 @@ __device__ __forceinline__ void publish_request(const FitArgs& a, int cs, int la
 // drained; the closing request has been sent).
 template <typename T, int K>
 __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, FitState& S, double* ws,
-                                          const double* cred, SeatBook& book, int* s_drained, uint64_t* part_bar,
+                                          const double* cred, SeatBook& book, volatile int* s_qcur, uint64_t* part_bar,
                                           uint32_t ctrl_addr, uint32_t req_bar_addr) {
   constexpr int W = fit_lanes<K>();
   const bool timing = a.phase_cycles != nullptr && lane == 0;
@@ -615,8 +631,10 @@ __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, Fi
     // lane 0 applies the penalty rule, lanes 1..k scale the gradient
     const double inv_n = 1.0 / (double)a.pts.n;
     double tot = 0.0;
-    if (lane <= K)
+    if (lane <= K) {
+#pragma unroll 8
       for (int r = 0; r < cs; ++r) tot += cred[r * (K + 1) + lane];
+    }
     const double f = a.O.loss_scale * (__shfl_sync(0xffffffffu, tot, 0) * inv_n);
     bool bad = !isfinite(f);
     if (a.O.stop_time < 1e8) {  // TimedFun: the clock starts at the first call
@@ -637,6 +655,7 @@ __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, Fi
     if (lane == 0) {
       S.rf = bad ? a.O.penalty : f;
       book.n_pass += 1;
+      if (timing) book.t_take += clock64() - ta;
     }
     __syncwarp();
   }
@@ -644,13 +663,15 @@ __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, Fi
   for (;;) {
     if (my_prog < 0) {  // empty seat: take the next run of the launch
       int r = -1;
-      if (!*s_drained) {
-        if (lane == 0) r = atomicAdd(a.queue, 1);
+      while (*s_qcur < a.n_queues) {
+        const int q = *s_qcur;
+        if (lane == 0) r = atomicAdd(a.queue + q, 1) + a.q_begin[q];
         r = __shfl_sync(0xffffffffu, r, 0);
-        if (r >= a.n_runs) {
-          *s_drained = 1;  // every lane, same value
-          r = -1;
-        }
+        if (r < a.q_end[q]) break;
+        __syncwarp();
+        if (lane == 0 && *s_qcur == q) *s_qcur = q + 1;  // drained (another seat's warp may have said so already)
+        __syncwarp();
+        r = -1;
       }
       if (r < 0) break;
       const int prog = a.run_prog[r];
@@ -674,12 +695,15 @@ __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, Fi
       if (lane == 0) {
         book.slot = slot;
         book.t0 = 0ull;
-        if (timing) book.t_seated = clock64(), book.t_logic = 0, book.n_pass = 0;
+        book.n_pass = 0;
+        if (timing) book.t_seated = clock64(), book.t_logic = 0, book.t_take = book.t_step = book.t_pub = 0, book.ns_seated = (long long)global_ns();
       }
       __syncwarp();
     }
+    const long long tb = timing ? clock64() : 0;
     const int act = fit_step_call<W>(S, a.O);
     __syncwarp();  // the state written back by the step is visible to every lane
+    if (timing) book.t_step += clock64() - tb;
     if (act == VSR_NEED_EVAL) break;
     // finished: results out, seat free, try to seat another run in this same turn
     if (lane == 0) {
@@ -704,7 +728,12 @@ __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, Fi
         ta = now;
         long long* ph = a.phase_cycles + (int64_t)slot * 8;
         ph[0] += book.t_logic;
+        ph[1] += book.t_take;
+        ph[2] += book.t_step;
+        ph[4] += book.t_pub;
         ph[3] += (now - book.t_seated) - book.t_logic;
+        ph[5] = book.ns_seated;
+        ph[6] = (long long)global_ns();
         ph[7] += book.n_pass;
       }
     }
@@ -719,8 +748,9 @@ __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, Fi
     if (my_prog >= 0) mbar_expect_tx(part_bar, (uint32_t)cs * (uint32_t)(K + 1) * 8u);
   }
   __syncwarp();
-  publish_request<T>(a, cs, lane, my_prog, my_k, fresh, ws /* S.xe() */, ctrl_addr, req_bar_addr);
-  if (timing && my_prog >= 0) book.t_logic += clock64() - ta;
+  const long long tp = timing ? clock64() : 0;
+  publish_request<T>(a, cs, lane, my_prog, my_k, fresh, (int)book.n_pass, ws /* S.xe() */, ctrl_addr, req_bar_addr);
+  if (timing && my_prog >= 0) book.t_logic += clock64() - ta, book.t_pub += clock64() - tp;
   return my_prog >= 0;
 }
 
@@ -734,7 +764,7 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   __shared__ __align__(8) uint64_t s_part_bar[kMaxSeats];  // totals of seat g's request have arrived (leader)
   __shared__ __align__(8) uint64_t s_bar;                  // TMA staging of the slice
   __shared__ int s_ticket[kMaxSeats];                      // sweeper warps of this CTA that finished seat g's requests
-  __shared__ int s_drained;
+  __shared__ int s_qcur;  // first queue of this launch that is not drained yet
 
   const int cs = (int)cluster.num_blocks();
   const int crank = (int)cluster.block_rank();
@@ -773,13 +803,14 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
     }
     mbar_init(&s_bar, 1);
     mbar_fence_init();
-    s_drained = 0;
+    s_qcur = 0;
   }
   if (tid < kMaxSeats) {
     s_book[tid].prog = -1;
     s_book[tid].k = 0;
     s_book[tid].t0 = 0ull;
     s_book[tid].t_logic = s_book[tid].t_seated = s_book[tid].n_pass = 0;
+    s_book[tid].t_take = s_book[tid].t_step = s_book[tid].t_pub = 0;
   }
   __syncthreads();
   if (a.resident) {
@@ -851,7 +882,7 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
         }
         double* seat = VSR_SEAT_STATE(g);
         const bool open = seat_turn<T, K>(a, lane, cs, *reinterpret_cast<FitState*>(seat), seat + kFitStateDoubles,
-                                          seat + a.off_cred, s_book[g], &s_drained, &s_part_bar[g],
+                                          seat + a.off_cred, s_book[g], &s_qcur, &s_part_bar[g],
                                           ctrl0 + 8u * (uint32_t)(g * seat_d), smem_u32(&s_req_bar[g]));
         if (open)
           opt_wait |= 1u << g;
@@ -860,16 +891,24 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
         progress = true;
       }
     }
-    // ---- sweeps of the seats whose request has arrived ----
+    // ---- one sweep: of the ready requests, the one of the OLDEST run ----
+    // (a run that has many passes behind it is probably on its way to the iteration cap, and the
+    // launch ends when the longest run does: it must not queue behind the young runs of its cluster)
     if (live) {
-      const bool only = !opt_live && (live & (live - 1)) == 0;
-      for (int g = 0; g < G; ++g) {
-        if (!((live >> g) & 1u)) continue;
-        const uint32_t par = (req_phase >> g) & 1u;
-        if (only)
-          mbar_wait(&s_req_bar[g], par);
-        else if (!mbar_test(&s_req_bar[g], par))
-          continue;
+      int g = -1;
+      if (!opt_live && (live & (live - 1)) == 0) {  // nothing else to do: block on the one live seat
+        g = __ffs(live) - 1;
+        mbar_wait(&s_req_bar[g], (req_phase >> g) & 1u);
+      } else {
+        int best_age = -1;
+        for (int q = 0; q < G; ++q) {
+          if (!((live >> q) & 1u) || !mbar_test(&s_req_bar[q], (req_phase >> q) & 1u)) continue;
+          const SeatCtrl* c = reinterpret_cast<const SeatCtrl*>(smem + (size_t)q * seat_d + a.off_ctrl);
+          const int age = c->prog < 0 ? 0x7fffffff : c->age;  // a closing request costs nothing: first
+          if (age > best_age) best_age = age, g = q;
+        }
+      }
+      if (g >= 0) {
         req_phase ^= 1u << g;
         progress = true;
         // the seat's code area through ONE opaque byte offset: without the asm the compiler
@@ -883,30 +922,30 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
         const SeatCtrl c = *reinterpret_cast<const SeatCtrl*>(c_imm - kSeatCstDoubles - kSeatCtrlDoubles);
         if (c.prog < 0) {  // the seat is closed
           live &= ~(1u << g);
-          continue;
-        }
-        if (a.resident)
-          sweep_slice<T, K, P>(c_insn, c_imm, c_cst, xs, ys, stride, cnt, scratch, stid, snt);
-        else
-          sweep_points<T, K, P>(c_insn, c_imm, c_cst, X, y, a.pts.ldx, n0, n1, scratch, stid, snt);
-        double* mine = wpart + ((size_t)g * nw + warp) * (K + 1);
-        warp_totals<K>(scratch, stid, snt, lane, mine);
-        __syncwarp();
-        int t = 0;
-        if (lane == 0) {
-          __threadfence_block();
-          t = atomicAdd(&s_ticket[g], 1);
-        }
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if ((t + 1) % nsw == 0) {
-          // last warp of this CTA for this request: the CTA's sums in warp order, to the leader
-          __threadfence_block();
-          if (lane <= K) {
-            const double* col = wpart + (size_t)g * nw * (K + 1) + lane;
-            double acc = 0.0;
-            for (int w = 0; w < nsw; ++w) acc += col[w * (K + 1)];
-            const uint32_t dst = smem_u32(VSR_SEAT_STATE(g) + a.off_cred + crank * (K + 1) + lane);
-            st_async_val(mapa_u32(dst, 0), acc, mapa_u32(smem_u32(&s_part_bar[g]), 0));
+        } else {
+          if (a.resident)
+            sweep_slice<T, K, P>(c_insn, c_imm, c_cst, xs, ys, stride, cnt, scratch, stid, snt);
+          else
+            sweep_points<T, K, P>(c_insn, c_imm, c_cst, X, y, a.pts.ldx, n0, n1, scratch, stid, snt);
+          double* mine = wpart + ((size_t)g * nw + warp) * (K + 1);
+          warp_totals<K>(scratch, stid, snt, lane, mine);
+          __syncwarp();
+          int t = 0;
+          if (lane == 0) {
+            __threadfence_block();
+            t = atomicAdd(&s_ticket[g], 1);
+          }
+          t = __shfl_sync(0xffffffffu, t, 0);
+          if ((t + 1) % nsw == 0) {
+            // last warp of this CTA for this request: the CTA's sums in warp order, to the leader
+            __threadfence_block();
+            if (lane <= K) {
+              const double* col = wpart + (size_t)g * nw * (K + 1) + lane;
+              double acc = 0.0;
+              for (int w = 0; w < nsw; ++w) acc += col[w * (K + 1)];
+              const uint32_t dst = smem_u32(VSR_SEAT_STATE(g) + a.off_cred + crank * (K + 1) + lane);
+              st_async_val(mapa_u32(dst, 0), acc, mapa_u32(smem_u32(&s_part_bar[g]), 0));
+            }
           }
         }
       }
