@@ -1,24 +1,35 @@
 #!/usr/bin/env python
 """Benchmark of the refinement hot path (BASELINE.json metric: candidate-fits/sec).
 
-Workload (config.workload): BASELINE config 2 -- AI-Feynman rows that tokenise with the
-shipped vocabulary, synthetic points from the table's ranges, beam = 64 candidates,
-10 restarts, 10 000 points, fp64.  A STEP is the refinement of one beam (what one
-``fitfunc2`` call hands to the BFGS part): 64 candidates x 10 restarts fitted and scored.
+A STEP is the refinement of one beam -- what one ``fitfunc2`` call hands to its BFGS part: C
+candidates x R restarts fitted over N points and scored.  ``--config`` selects the BASELINE.json
+workload (default 2, the one the metric is quoted on):
 
-  value   whole-job candidate-fits/s with points, programs and starting points already
-          resident in HBM when the timed region starts (device events, max over ranks)
-  e2e     the same through the C ABI with HOST buffers: upload points + programs +
-          starting points, fit, read every result back (vsr_upload_* + vsr_fit_host)
+  1  low_benchmarks.csv rows      C=16    R=10  N=500    fp64   (the only one the AS-IS reference runs)
+  2  AI-Feynman table rows        C=64    R=10  N=1e4    fp64
+  3  ODE-Strogatz (ode.xlsx)      C=128   R=32  N=1e4    fp64
+  4  SRSD-shaped Feynman (log-uniform ranges)  C=256  R=64  N=1e5  fp32 sweeps, fp64 optimiser state
+  5  black-box shaped, 3 variables, fp32 points  C=1024  R=10  N=--points (1e3 ... 1e7)
+
+  value   whole-job candidate-fits/s with points, programs and starting points already resident in
+          HBM when the timed region starts (device events, max over ranks)
+  e2e     the same steps through the entry point a driver calls, ``refine_hypotheses`` (token ids and
+          host tensors in, the reference's dict out): host->device copies, skeleton compilation
+          (cold cache), fit, prune, winner formatting and the device->host read all inside the
+          timed region.  ``e2e_abi`` is the C-ABI figure (vsr_upload_* + vsr_fit_host, host buffers,
+          precompiled bytecode).
   roofline / cpu_baseline: see DESIGN.md section "Measurement".
 
-`--impl reference` times the reference's CPU algorithm for this path (the oracle port:
-scipy BFGS over numpy columns, one process per host core as model.py:490 does) on a
-bounded sample of the same workload.
-N > 1 (torchrun): weak scaling = fixed work per GPU: the job is N times the `steps` beams of the
-one-GPU job; beams are independent units, every rank holds them resident and the ranks claim
-steps from one pool (own stripe first, then what the others have not started) -- no data-path
-collective.
+N > 1 (torchrun): STRONG scaling of the north-star partition -- every step is ONE beam whose
+(candidate, restart) runs are dealt over all ranks (engine/sharding.py), each rank fits its share, one
+all-gather of per-candidate records inside the timed region, same argmin everywhere; the winners
+are checked bit-for-bit against the one-GPU fit of the same beam in the run.  The throughput of N
+independent replica beams (no collective, weak scaling) is kept as the extra key ``replicas``.
+
+`--impl reference` times the reference's CPU implementation of the path on the host cores: the
+as-is reference (oracle/_ref, built by oracle/build_ref.py) for config 1, the oracle port (scipy
+BFGS over numpy columns -- the as-is reference cannot run at N >= ~1e4) for the others; one step =
+all candidates of one beam on all cores, one pool for the whole run.
 """
 import argparse
 import json
@@ -35,6 +46,19 @@ for p in (ROOT, os.path.join(ROOT, "vision-sr_b200")):
 
 import numpy as np  # noqa: E402
 
+CONFIGS = {
+    1: dict(table="low", points=500, cand=16, restarts=10, precision="fp64",
+            what="low_benchmarks.csv rows (Nguyen-style, 1-2 variables)"),
+    2: dict(table="feynman", points=10_000, cand=64, restarts=10, precision="fp64",
+            what="AI-Feynman table rows (FeynmanEquations.xlsx)"),
+    3: dict(table="ode", points=10_000, cand=128, restarts=32, precision="fp64",
+            what="ODE-Strogatz rows (ode.xlsx), x_1, x_2 ~ U(0.1, 5)"),
+    4: dict(table="srsd", points=100_000, cand=256, restarts=64, precision="fp32",
+            what="SRSD-Feynman-shaped: Feynman rows, variables log-uniform over two decades"),
+    5: dict(table="blackbox", points=100_000, cand=1024, restarts=10, precision="fp32",
+            what="black-box shaped: X ~ N(0,1) in 3 variables (fp32), y = 1.5 x1 sin(0.7 x2) + 0.3 x3^2 + noise"),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -42,15 +66,26 @@ def parse():
     ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--points", type=int, default=10_000)
-    ap.add_argument("--cand", type=int, default=64)
-    ap.add_argument("--restarts", type=int, default=10)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--points", type=int, default=0, help="override the config's number of points")
+    ap.add_argument("--cand", type=int, default=0, help="override the config's beam size")
+    ap.add_argument("--restarts", type=int, default=0, help="override the config's number of restarts")
     ap.add_argument("--grad-mode", default="dual", choices=["dual", "fd"])
-    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
+    ap.add_argument("--precision", default="", choices=["", "fp64", "fp32"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "sharded", "replicas"],
+                    help="N > 1: one beam sharded over the ranks (auto) or independent replica beams")
     ap.add_argument("--warps", type=int, default=0)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the CPU baseline sample (0 = 2 per core)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-api", action="store_true", help="skip the refine_hypotheses end-to-end loop")
+    ap.add_argument("--rows", default="", help="comma separated table row names (default: table order)")
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    a.points = a.points or c["points"]
+    a.cand = a.cand or c["cand"]
+    a.restarts = a.restarts or c["restarts"]
+    a.precision = a.precision or c["precision"]
+    return a
 
 
 # ---- workload (generated in parallel: sympy is slow) -----------------------------------------
@@ -58,70 +93,74 @@ def _gen_beam(job):
     import warnings
     warnings.filterwarnings("ignore")
     from src.visymre.workloads import generator as g
-    e, row, n_points, n_cand, n_restarts = job
+    table, e, row, n_points, n_cand, n_restarts = job
     td = g.make_test_data()
-    b = g.build_beam(e, row["name"], row["replaced"] or row["formula"], row["variables"], n_points,
-                     n_cand, n_restarts, td)
+    if table in ("feynman", "srsd"):
+        b = g.build_beam(e + (50_000 if table == "srsd" else 0), row["name"], row["replaced"] or row["formula"],
+                         row["variables"], n_points, n_cand, n_restarts, td, log_uniform=(table == "srsd"))
+    elif table == "low":
+        b = g.low_beam(e, row, n_points, n_cand, n_restarts, td)
+    elif table == "ode":
+        b = g.build_beam(20_000 + e, row["name"], row["formula"], [dict(low=0.1, high=5.0)] * 2,
+                         n_points, n_cand, n_restarts, td)
+    else:
+        b, _ = g.blackbox_beam(n_points, n_cand, n_restarts, seed=e)
     if b is None:
         return None
     g.compile_beam(b, td)
     return b
 
 
-def make_workload(n_beams, n_points, n_cand, n_restarts, offset=0, stride=1):
-    """Beams offset, offset+stride, ... of the Feynman table (only rows that tokenise)."""
-    from concurrent.futures import ProcessPoolExecutor
+def table_rows(args):
     from src.visymre.workloads import generator as g
     t = g.load_tables()
-    rows = [(e, r) for e, r in enumerate(t["feynman"]) if not r["name"].startswith("test_")]
-    rows = rows[offset::stride]
-    jobs = [(e, r, n_points, n_cand, n_restarts) for e, r in rows]
-    beams = []
-    workers = max(1, min(32, (os.cpu_count() or 2) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
+    table = CONFIGS[args.config]["table"]
+    if table in ("feynman", "srsd"):
+        rows = [(e, r) for e, r in enumerate(t["feynman"]) if not r["name"].startswith("test_")]
+    elif table == "low":
+        rows = list(enumerate(t["low"]))
+    elif table == "ode":
+        rows = list(enumerate(t["ode"]))
+    else:
+        rows = [(0, dict(name="blackbox"))]
+    if args.rows:
+        want = args.rows.split(",")
+        rows = [(e, r) for e, r in rows if r["name"] in want]
+    return table, rows
+
+
+def make_workload(n_beams, args, *legacy, rank=0, world=1, dist=None):
+    """The first n_beams usable rows of the config's table, one beam each (cycled when the table is
+    shorter).  With several ranks every rank generates rows rank, rank+world, ... with its share of the
+    host cores and one all_gather_object puts the lists together: every rank holds the same beams."""
+    from concurrent.futures import ProcessPoolExecutor
+    if isinstance(args, int):   # make_workload(n, points, cand, restarts): config 2 at the given sizes
+        args = argparse.Namespace(config=2, points=args, cand=legacy[0], restarts=legacy[1], rows="")
+    table, rows = table_rows(args)
+    rows = rows[: int(n_beams * 1.3) + 4]
+    jobs = [(table, e, r, args.points, args.cand, args.restarts) for e, r in rows]
+    workers = max(1, min(32, (os.cpu_count() or 2) // world, len(jobs)))
+    mine = jobs[rank::world]
     with ProcessPoolExecutor(workers) as ex:
-        for b in ex.map(_gen_beam, jobs[: int(n_beams * 1.3) + 4]):
-            if b is not None:
-                beams.append(b)
-            if len(beams) >= n_beams:
-                break
+        got = list(ex.map(_gen_beam, mine))
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, got)
+        got = [parts[i % world][i // world] for i in range(len(jobs))]
+    beams = [b for b in got if b is not None]
     if not beams:
         raise RuntimeError("no beam could be generated")
+    distinct = len(beams)
     while len(beams) < n_beams:      # fewer usable rows than steps: cycle
-        beams.append(beams[len(beams) % len(beams)])
+        beams.append(beams[len(beams) % distinct])
     return beams[:n_beams]
 
 
-def make_shared_workload(n_distinct, n_points, n_cand, n_restarts, rank, world, dist):
-    """The same list of distinct beams on every rank: rank r generates rows r, r+world, ... with its
-    share of the host cores, one all_gather_object puts the lists together (row order)."""
-    from concurrent.futures import ProcessPoolExecutor
-    from src.visymre.workloads import generator as g
-    t = g.load_tables()
-    rows = [(e, r) for e, r in enumerate(t["feynman"]) if not r["name"].startswith("test_")]
-    rows = rows[: int(n_distinct * 1.3) + 4]
-    mine = rows[rank::world]
-    jobs = [(e, r, n_points, n_cand, n_restarts) for e, r in mine]
-    workers = max(1, min(32, (os.cpu_count() or 2) // world))
-    with ProcessPoolExecutor(workers) as ex:
-        got = list(ex.map(_gen_beam, jobs))
-    parts = [None] * world
-    dist.all_gather_object(parts, got)
-    beams = []
-    for i in range(len(rows)):          # back to row order
-        b = parts[i % world][i // world]
-        if b is not None:
-            beams.append(b)
-    if not beams:
-        raise RuntimeError("no beam could be generated")
-    return beams[:n_distinct] if len(beams) >= n_distinct else beams
-
-
 class Claims:
-    """Hands out the global step indices 0..n-1 of the job to the ranks of ONE node: rank r takes its
-    own stripe r, r+world, ... first and then what the others have not started yet (from the end of
-    their stripes).  A claim is an O_EXCL file creation in a directory all ranks see; with one
-    rank it is a plain counter.  Beams are independent units: this is scheduling, not a data-path
-    collective, and it keeps one rank with unlucky (long) beams from holding the job up."""
+    """Replica mode: hands out the global step indices 0..n-1 to the ranks of ONE node: rank r takes its
+    own stripe r, r+world, ... first and then what the others have not started yet.  A claim is an
+    O_EXCL file creation in a directory all ranks see; with one rank it is a plain counter.  Beams
+    are independent units: this is scheduling, not a data-path collective."""
 
     def __init__(self, n, rank, world, root, tag):
         self.n, self.rank, self.world, self.root, self.tag = n, rank, world, root, tag
@@ -179,80 +218,145 @@ class ClockSampler:
                 "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(rows)}
 
 
-# ---- CPU baseline (oracle port of the reference's path) ------------------------------------------
+# ---- CPU arm: the reference's path on the host cores ----------------------------------------------
 def _cpu_fit(job):
+    """One candidate through the CPU implementation.  kind 'port': oracle/vectorised.py; kind
+    'reference': the unmodified reference's own bfgs_wrapper (oracle/_ref or /root/reference), with
+    its per-restart np.random.randn draws fed from the workload's starting points."""
     import warnings
     warnings.filterwarnings("ignore")
-    from oracle import vectorised
-    from src.visymre.workloads import generator as g
-    tokens, X, y, x0, R = job
-    td = g.make_test_data()
-    cfg = g.make_cfg(R)
-    rec = vectorised.Recorder()
-    out = vectorised.bfgs_wrapper((tokens, X[None], y, cfg, td), x0=x0, record=rec)
-    nfev = sum(r.get("nfev", 0) for r in rec.restarts)
-    return out[1], nfev
+    kind, tokens, X, y, x0, R = job
+    if kind == "port":
+        from oracle import vectorised
+        from src.visymre.workloads import generator as g
+        rec = vectorised.Recorder()
+        out = vectorised.bfgs_wrapper((tokens, X[None], y, g.make_cfg(R), g.make_test_data()), x0=x0, record=rec)
+        return out[1], sum(r.get("nfev", 0) for r in rec.restarts)
+    import torch
+    from types import SimpleNamespace as NS
+    from oracle import ref_harness
+    # the reference's `src` is a namespace package and this repo's a regular one, which would win
+    # whatever the order of sys.path: this worker process only ever runs the reference
+    sys.path[:] = [p for p in sys.path if os.path.basename(p.rstrip("/")) != "vision-sr_b200"]
+    ref_bfgs, ref_model, td = ref_harness.load()
+    cfg = NS(bfgs=NS(n_restarts=R, add_coefficients_if_not_existing=False, idx_remove=False,
+                     normalization_type="MSE", stop_time=1e9))
+    nfev = [0]
+    real_minimize, real_randn = ref_bfgs.minimize, np.random.randn
+    draws = [np.asarray(r, dtype=np.float64) / 10.0 for r in x0]
+
+    def counting(fun, start, **kw):
+        res = real_minimize(fun, start, **kw)
+        nfev[0] += int(res.nfev)
+        return res
+
+    def fed(*shape):
+        return draws.pop(0).copy() if draws and len(draws[0]) == (shape[0] if shape else 1) else real_randn(*shape)
+    ref_bfgs.minimize, ref_bfgs.np.random.randn = counting, fed
+    try:
+        out = ref_model.bfgs_wrapper((list(tokens), torch.tensor(X[None]), torch.tensor(y), cfg, td))
+    finally:
+        ref_bfgs.minimize, ref_bfgs.np.random.randn = real_minimize, real_randn
+    return out[1], nfev[0]
 
 
-def cpu_baseline(beams, R, n_sample, cores=None):
-    """candidate-fits/s of the oracle port on `cores` host processes, bounded sample."""
-    from concurrent.futures import ProcessPoolExecutor
-    cores = cores or min(os.cpu_count() or 1, 64)
-    n_sample = n_sample or 2 * cores
-    jobs = []
-    bi = 0
-    while len(jobs) < n_sample:
-        b = beams[bi % len(beams)]
-        for j in range(len(b.tokens)):
-            jobs.append((b.tokens[j], b.X, b.y, b.x0[j], R))
-            if len(jobs) >= n_sample:
-                break
-        bi += 1
-    with ProcessPoolExecutor(cores) as ex:
-        list(ex.map(_cpu_fit, jobs[:cores]))  # warm the workers (imports)
+def cpu_kind(args):
+    """Which CPU implementation this config is timed on, and why."""
+    if args.config == 1:
+        sys.path.insert(0, ROOT)
+        from oracle import ref_harness
+        if ref_harness.available():
+            return "reference"
+    return "port"
+
+
+class CpuArm:
+    """One worker pool for a whole run; a step = all candidates of a beam."""
+
+    def __init__(self, kind, R):
+        from concurrent.futures import ProcessPoolExecutor
+        import multiprocessing as mp
+        self.kind, self.R = kind, R
+        self.cores = min(os.cpu_count() or 1, 64)
+        # spawn: the parent may hold a CUDA context, and the as-is reference must not meet this
+        # repo's `src` package (same top-level name) in its process
+        self.pool = ProcessPoolExecutor(self.cores, mp_context=mp.get_context("spawn"))
+        list(self.pool.map(_noop, range(2 * self.cores)))   # start the workers before any timing
+
+    def step(self, beam, limit=None):
+        jobs = [(self.kind, beam.tokens[j], beam.X, beam.y, beam.x0[j], self.R)
+                for j in range(len(beam.tokens) if limit is None else min(limit, len(beam.tokens)))]
         t0 = time.time()
-        outs = list(ex.map(_cpu_fit, jobs))
+        outs = list(self.pool.map(_cpu_fit, jobs))
         dt = time.time() - t0
-    nfev = sum(o[1] for o in outs)
+        return len(jobs), dt, sum(o[1] for o in outs)
+
+    def close(self):
+        self.pool.shutdown(wait=False, cancel_futures=True)
+
+
+def _noop(i):
+    import numpy  # noqa: F401
+    return i
+
+
+def cpu_baseline(beams, args, budget_s):
+    """candidate-fits/s of the CPU arm on whole beams of the timed workload, until the budget is spent."""
+    kind = cpu_kind(args)
+    arm = CpuArm(kind, args.restarts)
+    arm.step(beams[0], limit=arm.cores)        # imports / first-call costs, untimed
+    n = dt = nfev = 0
+    t_all = time.time()
+    used = 0
+    for b in beams:
+        a, d, f = arm.step(b)
+        n, dt, nfev, used = n + a, dt + d, nfev + f, used + 1
+        if time.time() - t_all > budget_s:
+            break
+    arm.close()
     N = beams[0].X.shape[0]
-    return {"value": len(jobs) / dt, "unit": "candidate-fits/s", "cores": cores, "kind": "port",
-            "sample": f"{len(jobs)} candidates of the same workload (R={R}, N={N}), oracle/vectorised.py "
-                      f"(scipy BFGS over numpy columns) in {cores} processes, {dt:.1f} s",
-            "point_evals_per_s": nfev * N / dt}
+    return {"value": n / dt, "unit": "candidate-fits/s", "cores": arm.cores, "kind": kind,
+            "sample": f"all {len(beams[0].tokens)} candidates of the first {used} timed beams (R={args.restarts}, N={N}), "
+                      + ("the unmodified reference's bfgs_wrapper (oracle/_ref)" if kind == "reference"
+                         else "oracle/vectorised.py (scipy BFGS over numpy columns)")
+                      + f" in {arm.cores} worker processes, {dt:.1f} s, nfev {nfev}",
+            "seconds": dt, "nfev": nfev, "point_evals_per_s": nfev * N / dt}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    beams = make_workload(max(2, min(8, args.steps)), args.points, args.cand, args.restarts)
-    cores = min(os.cpu_count() or 1, 64)
-    per_step = max(cores, 8)
-    vals = []
+    beams = make_workload(args.warmup + args.steps, args)
+    kind = cpu_kind(args)
+    arm = CpuArm(kind, args.restarts)
+    n = dt = nfev = steps = 0
     t_all = time.time()
     for s in range(args.warmup + args.steps):
-        b = beams[s % len(beams)]
-        sub = [type(b)(name=b.name, X=b.X, y=b.y, tokens=b.tokens[:per_step], x0=b.x0[:per_step])]
-        r = cpu_baseline(sub, args.restarts, per_step, cores)
+        a, d, f = arm.step(beams[s])
         if s >= args.warmup:
-            vals.append(r)
-        if time.time() - t_all > 240:
+            n, dt, nfev, steps = n + a, dt + d, nfev + f, steps + 1
+        if time.time() - t_all > 240 and steps >= 2:
             break
-    v = float(np.mean([r["value"] for r in vals]))
+    arm.close()
+    v = n / dt
     line = {"impl": "reference", "metric": "candidate_fits_per_sec", "value": v, "unit": "candidate-fits/s",
-            "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
-            "ms_per_step": 1e3 * per_step / v, "higher_is_better": True, "scaling": "weak",
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args),
-            "cpu_baseline": {"value": v, "unit": "candidate-fits/s", "cores": cores, "kind": "port",
-                             "sample": f"{per_step} candidates per step, {len(vals)} steps"},
+            "cpu_baseline": {"value": v, "unit": "candidate-fits/s", "cores": arm.cores, "kind": kind,
+                             "sample": f"all {args.cand} candidates of {steps} beams, one pool of {arm.cores} worker processes, "
+                                       f"{dt:.1f} s, nfev {nfev}", "seconds": dt, "nfev": nfev},
             "e2e": {"value": v, "unit": "candidate-fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def workload_config(args):
-    return {"workload": "BASELINE config 2: AI-Feynman table rows (FeynmanEquations.xlsx), synthetic points, "
-                        f"beam={args.cand}, restarts={args.restarts}, points={args.points}; one step = one beam",
+    c = CONFIGS[args.config]
+    return {"workload": f"BASELINE config {args.config}: {c['what']}, synthetic points, beam={args.cand}, "
+                        f"restarts={args.restarts}, points={args.points}; one step = one beam",
+            "baseline_config": args.config,
             "candidates_per_step": args.cand, "restarts": args.restarts, "points": args.points,
             "grad_mode": args.grad_mode, "precision": args.precision,
             "l2": "flushed between timed steps (256 MiB write)"}
@@ -265,7 +369,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from src.visymre.engine import fitter, isa
+    from src.visymre.engine import fitter, hostpool, isa, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -274,45 +378,36 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    mode = args.mode if args.mode != "auto" else ("sharded" if world > 1 else "replicas")
+    if world == 1:
+        mode = "replicas"
 
-    # The job is world x steps beams (weak scaling).  Every rank holds the distinct beams of the job
-    # resident and the ranks claim steps from one pool (class Claims): step i of the job is beam
-    # job[i].  With one rank this is the plain sequence warmup beams, then the timed beams.
-    n_job = world * args.steps
-    if world > 1:
-        beams = make_shared_workload(args.warmup + args.steps, args.points, args.cand, args.restarts, rank, world, dist)
-        claim_root = [None]
-        if rank == 0:
-            import tempfile
-            claim_root[0] = tempfile.mkdtemp(prefix="vsr_bench_")
-        dist.broadcast_object_list(claim_root, src=0)
-        claim_root = claim_root[0]
-    else:
-        beams = make_workload(args.warmup + args.steps, args.points, args.cand, args.restarts)
-        claim_root = None
+    # ---- workload: warmup + steps distinct beams, the same on every rank ----
+    beams = make_workload(args.warmup + args.steps, args, rank=rank, world=world, dist=dist if world > 1 else None)
     D = len(beams)
-    # weak scaling = fixed work per GPU: the job at N GPUs is N times the `steps` beams of the
-    # one-GPU job (every repetition is a full, independent refinement)
-    job = [(args.warmup + (i % args.steps)) % D for i in range(n_job)]   # beam index of every timed step
+    timed = [(args.warmup + i) % D for i in range(args.steps)]   # beam index of timed step i
     warm = [s % D for s in range(args.warmup)]
     R, C = args.restarts, args.cand
     eval_dt = fitter.F32 if args.precision == "fp32" else fitter.F64
+    x_is_f32 = beams[0].X.dtype == np.float32
+    score_dt = fitter.F32 if x_is_f32 else fitter.F64
     opts = fitter.default_opts(grad_mode=isa.GRAD_MODE["VSR_GRAD_FD" if args.grad_mode == "fd" else "VSR_GRAD_DUAL"],
-                               eval_dtype=eval_dt, score_dtype=fitter.F64, warps_per_run=args.warps)
+                               eval_dtype=eval_dt, score_dtype=score_dt, warps_per_run=args.warps)
 
-    # ---- resident setup: one engine per beam, everything uploaded before timing ----
-    setups = []
-    for b in beams:
+    # ---- resident setup: one engine per distinct beam, everything uploaded before timing ----
+    setups = {}
+    for bi in sorted(set(timed + warm)):
+        b = beams[bi]
         eng = fitter.Engine(dev)
-        eng.set_points(b.X, b.y, dtypes=tuple({eval_dt, fitter.F64}))
+        eng.set_points(b.X, b.y, dtypes=tuple({eval_dt, score_dt}))
         eng.set_programs(b.programs)
         kmax = max(1, max(p.k for p in b.programs))
         x0 = np.zeros((C * R, kmax))
         for j in range(C):
             x0[j * R:(j + 1) * R, :b.x0[j].shape[1]] = b.x0[j]
-        run_prog = np.repeat(np.arange(C), R)
-        run_slot = np.arange(C * R)
-        setups.append((eng, torch.from_numpy(x0).to(dev), run_prog, run_slot, x0))
+        cost = np.repeat([(p.k + 1.0) * p.n_insns for p in b.programs], R)
+        setups[bi] = dict(eng=eng, x0d=torch.from_numpy(x0).to(dev), rp=np.repeat(np.arange(C), R),
+                          rs=np.arange(C * R), x0h=x0, ks=[p.k for p in b.programs], cost=cost)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
 
@@ -322,49 +417,78 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: device-resident steps ----
+    def fit_step(su):
+        """One step on the device-resident data: the whole beam (one GPU / replica) or this rank's
+        share of it plus the all-gather of the per-candidate records (sharded)."""
+        if mode == "sharded":
+            return sharding.fit_sharded(su["eng"], su["ks"], R, su["x0d"], opts, cost=su["cost"],
+                                        key_dtype=torch.float32 if score_dt == fitter.F32 else None)
+        return None, su["eng"].fit(su["rp"], su["rs"], su["x0d"], opts)
+
     import gc
     gc.collect()
     gc.disable()   # a generation-2 collection over sympy's object graph stalls the host for ~50-100 ms
     for bi in warm:
-        eng, x0d, rp, rs, _ = setups[bi]
-        eng.fit(rp, rs, x0d, opts)
+        fit_step(setups[bi])
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     t_wall0 = time.time()
-    launches0 = sum(s[0].launches for s in setups)
-    claims = Claims(n_job, rank, world, claim_root, "v")
+    launches0 = sum(s["eng"].launches for s in setups.values())
+
+    # ---- value: device-resident steps ----
+    claim_root = None
+    if world > 1 and mode == "replicas":
+        claim_root = [None]
+        if rank == 0:
+            import tempfile
+            claim_root[0] = tempfile.mkdtemp(prefix="vsr_bench_")
+        dist.broadcast_object_list(claim_root, src=0)
+        claim_root = claim_root[0]
+    n_job = args.steps if mode == "sharded" else world * args.steps
+    job = [timed[i % args.steps] for i in range(n_job)]
     prof = [0.0, 0.0, 0.0, 0.0]
-    mine, ev, results = [], [], []           # the steps this rank ran: beam index, events, result
-    while True:
-        i = claims.next()
-        if i is None:
-            break
-        bi = job[i]
-        eng, x0d, rp, rs, _ = setups[bi]
-        eng.set_profiling(True)
-        flush.fill_(i & 0xFF)          # evict the previous step's data from L2 (untimed)
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        res = eng.fit(rp, rs, x0d, opts)
-        b_.record()
-        # a driver needs the result of one beam before it decodes the next; it also keeps the
-        # next step's launches out of the hardware queues while this one runs (enqueueing all
-        # steps back to back made every step ~10 % slower, tools/exp_valueloop.py)
-        torch.cuda.synchronize()
-        mine.append(bi)
-        ev.append((a, b_))
-        results.append(res)
-        p = eng.read_profile()         # per step: an engine can serve several steps of the job
-        eng.set_profiling(False)
-        prof = [x + y for x, y in zip(prof, p)]
+    mine, ev, results, winners = [], [], [], []
+
+    def timed_loop(tag):
+        claims = Claims(n_job, rank, world, claim_root, tag) if mode == "replicas" else None
+        i_seq = 0
+        while True:
+            if mode == "replicas":
+                i = claims.next()
+                if i is None:
+                    break
+            else:
+                if i_seq >= n_job:
+                    break
+                i, i_seq = i_seq, i_seq + 1
+            su = setups[job[i]]
+            su["eng"].set_profiling(True)
+            flush.fill_(i & 0xFF)          # evict the previous step's data from L2 (untimed)
+            if mode == "sharded":
+                barrier()                  # every rank starts the beam together (untimed)
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            win, res = fit_step(su)
+            b_.record()
+            # a driver needs the result of one beam before it decodes the next
+            torch.cuda.synchronize()
+            mine.append(job[i])
+            ev.append((a, b_))
+            results.append(res)
+            winners.append(win)
+            p = su["eng"].read_profile()
+            su["eng"].set_profiling(False)
+            for q in range(4):
+                prof[q] += p[q]
+
+    timed_loop("v")
     barrier()
     t_wall1 = time.time()
     step_ms = [a.elapsed_time(b_) for a, b_ in ev]
     total_ms = float(sum(step_ms))
-    print(f"rank {rank}: {len(mine)} steps, {total_ms:.1f} ms: " + " ".join(f"{beams[bi].name}:{m:.1f}" for bi, m in zip(mine, step_ms)),
-          file=sys.stderr)
-    launches = sum(s[0].launches for s in setups) - launches0
+    print(f"rank {rank} [{mode}]: {len(mine)} steps, {total_ms:.1f} ms: "
+          + " ".join(f"{beams[bi].name}:{m:.1f}" for bi, m in zip(mine, step_ms)), file=sys.stderr)
+    launches = sum(s["eng"].launches for s in setups.values()) - launches0
     fit_ms, fit_n, score_ms = prof[0], prof[1], prof[2]
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 
@@ -376,93 +500,147 @@ def main():
         info = results[i].info.cpu().numpy().reshape(C, R, 4)
         N = b.X.shape[0]
         for j, p in enumerate(b.programs):
-            nfev = float(info[j, :, 2].sum())
+            nf = info[j, :, 2]
+            nfev = float(nf[nf > 0].sum())       # slots other ranks fitted read -1 here
             per_pass = (1 + p.k) if args.grad_mode == "dual" else 1
             pevals += nfev * N * per_pass
             flops += nfev * N * per_pass * p.flops
             d_used = bin(p.var_mask).count("1")
             abytes += nfev * (N * (d_used + 1) * es + (1 + p.k) * 8)
 
-    # ---- e2e: host buffers through the C ABI (uploads + fit + read-back), same steps ----
-    # ONE engine for all steps, as a driver process has (fitter.get_engine is process-wide): its
-    # device buffers are allocated by the first (untimed) steps and reused afterwards
-    e2e_ms, h2d, d2h = 0.0, 0, 0
-    e2e_eng = fitter.Engine(dev)
-    e2e_claims = Claims(n_job, rank, world, claim_root, "e")
-    e2e_warm = list(warm[-min(2, len(warm)):])
-    barrier()
-    while True:
-        if e2e_warm:
-            bi, timed = e2e_warm.pop(0), False
-        else:
-            i = e2e_claims.next()
-            if i is None:
-                break
-            bi, timed = job[i], True
-        n_vars_i = setups[bi][0].n_vars
-        _, _, rp, rs, x0h = setups[bi]
-        eng = e2e_eng
-        b = beams[bi]
-        Xc = np.ascontiguousarray(b.X[:, :n_vars_i].T)  # column-major host copy (layout prepared once)
-        yh = np.ascontiguousarray(b.y)
-        insn_off = np.zeros(C + 1, dtype=np.int32)
-        imm_off = np.zeros(C + 1, dtype=np.int32)
-        for j, p in enumerate(b.programs):
-            insn_off[j + 1] = insn_off[j] + p.insns.shape[0]
-            imm_off[j + 1] = imm_off[j] + p.imms.shape[0]
-        insns = np.concatenate([p.insns for p in b.programs]).astype(np.uint64)
-        imms = np.concatenate([p.imms for p in b.programs]).astype(np.float64)
-        ks = np.asarray([p.k for p in b.programs], dtype=np.int32)
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        st = eng._stream()
-        vp = lambda a: a.ctypes.data_as(fitter.ctypes.c_void_p)  # noqa: E731
-        eng._check(eng.lib.vsr_upload_points(eng._h, vp(Xc), vp(yh), Xc.shape[1], Xc.shape[1], Xc.shape[0],
-                                             fitter.F64, st))
-        t1 = time.perf_counter()
-        eng._check(eng.lib.vsr_upload_programs(eng._h, vp(insns), vp(insn_off), vp(imms), vp(imm_off), vp(ks), C, st))
-        eng._points = {fitter.F64: None}   # the points went in through the C ABI, not through set_points
-        t2 = time.perf_counter()
-        o64 = fitter.default_opts(grad_mode=opts.grad_mode, eval_dtype=fitter.F64, score_dtype=fitter.F64,
-                                  warps_per_run=args.warps)
-        out = eng.fit_host(rp, rs, x0h, o64)
-        dt = (time.perf_counter() - t0) * 1e3
-        if timed:
-            e2e_ms += dt
-            if rank == 0:
-                print(f"e2e_ms {b.name}:{dt:.1f} (points {1e3 * (t1 - t0):.1f} programs {1e3 * (t2 - t1):.1f})", file=sys.stderr)
-            h2d = Xc.nbytes + yh.nbytes + insns.nbytes + imms.nbytes + insn_off.nbytes + imm_off.nbytes + ks.nbytes + x0h.nbytes + rp.nbytes // 2 + rs.nbytes // 2
-            d2h = sum(v.nbytes for v in out.values())
+    # ---- sharded: the winners equal the one-GPU answer, bit for bit (checked outside the timing) ----
+    shard_check = None
+    if mode == "sharded":
+        bad = 0
+        n_chk = min(len(mine), 4)
+        for i in range(n_chk):
+            su = setups[mine[i]]
+            full = su["eng"].fit(su["rp"], su["rs"], su["x0d"], opts)
+            fm = full.final_mse.cpu().numpy().reshape(C, R)
+            if score_dt == fitter.F32:
+                fm = fm.astype(np.float32)
+            lx = full.lastx.cpu().numpy().reshape(C, R, -1)
+            w = winners[i].cpu().numpy()
+            for c in range(C):
+                want = 0 if np.all(np.isnan(fm[c])) else int(np.nanargmin(fm[c]))
+                if int(w[c, 1]) != want or not np.array_equal(w[c, 3:3 + lx.shape[2]], lx[c, want], equal_nan=True):
+                    bad += 1
+        t_bad = torch.tensor([bad], device=dev)
+        dist.all_reduce(t_bad)
+        shard_check = {"beams_checked": n_chk, "candidates_differing_from_one_gpu": int(t_bad.item())}
 
-    gc.enable()
-    # ---- the Python entry point a driver calls: tokens in, dict out (sympy compile + fit +
-    #      winner formatting), a few beams, cold compile cache ----
-    api_ms, api_n = 0.0, 0
+    # ---- replicas extra at N > 1 (weak scaling of independent beams, no collective) ----
+    replicas = None
+    if world > 1 and mode == "sharded":
+        mode_saved, mode = mode, "replicas"
+        claim_root = [None]
+        if rank == 0:
+            import tempfile
+            claim_root[0] = tempfile.mkdtemp(prefix="vsr_bench_")
+        dist.broadcast_object_list(claim_root, src=0)
+        claim_root = claim_root[0]
+        n_job_saved, job_saved = n_job, job
+        n_job = world * args.steps
+        job = [timed[i % args.steps] for i in range(n_job)]
+        keep = (list(mine), list(ev), list(results), list(winners))
+        mine.clear(); ev.clear(); results.clear(); winners.clear()
+        barrier()
+        timed_loop("r")
+        barrier()
+        rep_ms = float(sum(a.elapsed_time(b_) for a, b_ in ev))
+        t_rep = torch.tensor([rep_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_rep, op=dist.ReduceOp.MAX)
+        replicas = {"value": world * args.steps * C / (t_rep.item() / 1e3), "unit": "candidate-fits/s", "scaling": "weak",
+                    "what": f"{world} x {args.steps} independent beams claimed from one pool, no data-path collective"}
+        mine[:], ev[:], results[:], winners[:] = keep
+        mode, n_job, job = mode_saved, n_job_saved, job_saved
+
+    # ---- e2e_abi: host buffers through the C ABI (uploads + fit + read-back), one GPU's view ----
+    abi_ms, h2d_abi, d2h_abi = 0.0, 0, 0
     if rank == 0:
+        e2e_eng = fitter.Engine(dev)
+        seq = list(warm[-min(2, len(warm)):]) + [timed[i] for i in range(min(args.steps, 8))]
+        n_warm = len(seq) - min(args.steps, 8)
+        for pos, bi in enumerate(seq):
+            su, b = setups[bi], beams[bi]
+            n_vars_i = su["eng"].n_vars
+            Xc = np.ascontiguousarray(b.X[:, :n_vars_i].T.astype(np.float64))  # column-major host copy
+            yh = np.ascontiguousarray(b.y.astype(np.float64))
+            insn_off = np.zeros(C + 1, dtype=np.int32)
+            imm_off = np.zeros(C + 1, dtype=np.int32)
+            for j, p in enumerate(b.programs):
+                insn_off[j + 1] = insn_off[j] + p.insns.shape[0]
+                imm_off[j + 1] = imm_off[j] + p.imms.shape[0]
+            insns = np.concatenate([p.insns for p in b.programs]).astype(np.uint64)
+            imms = np.concatenate([p.imms for p in b.programs]).astype(np.float64)
+            ks = np.asarray([p.k for p in b.programs], dtype=np.int32)
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            st = e2e_eng._stream()
+            vp = lambda a: a.ctypes.data_as(fitter.ctypes.c_void_p)  # noqa: E731
+            e2e_eng._check(e2e_eng.lib.vsr_upload_points(e2e_eng._h, vp(Xc), vp(yh), Xc.shape[1], Xc.shape[1],
+                                                         Xc.shape[0], fitter.F64, st))
+            e2e_eng._check(e2e_eng.lib.vsr_upload_programs(e2e_eng._h, vp(insns), vp(insn_off), vp(imms), vp(imm_off),
+                                                           vp(ks), C, st))
+            e2e_eng._points = {fitter.F64: None}   # the points went in through the C ABI, not through set_points
+            o64 = fitter.default_opts(grad_mode=opts.grad_mode, eval_dtype=fitter.F64, score_dtype=fitter.F64,
+                                      warps_per_run=args.warps)
+            out = e2e_eng.fit_host(su["rp"], su["rs"], su["x0h"], o64)
+            dt = (time.perf_counter() - t0) * 1e3
+            if pos >= n_warm:
+                abi_ms += dt
+                h2d_abi = (Xc.nbytes + yh.nbytes + insns.nbytes + imms.nbytes + insn_off.nbytes + imm_off.nbytes
+                           + ks.nbytes + su["x0h"].nbytes + su["rp"].nbytes // 2 + su["rs"].nbytes // 2)
+                d2h_abi = sum(v.nbytes for v in out.values())
+        abi_n = min(args.steps, 8)
+        e2e_eng.close()
+
+    # ---- e2e: the Python entry point a driver calls (tokens + HOST tensors in, dict out) ----
+    api_ms, api_n, h2d, d2h = 0.0, 0, 0, 0
+    if not args.no_api:
+        from src.visymre.architectures import bfgs as vbfgs
         from src.visymre.architectures.model import refine_hypotheses
         from src.visymre.workloads import generator as g
         td = g.make_test_data()
-        cfg = g.make_cfg(R, C, grad_mode=args.grad_mode)
-        for i in range(min(args.steps, 4)):
-            b = beams[job[i]]
-            Xd = torch.from_numpy(b.X[None]).to(dev)
-            yd = torch.from_numpy(b.y).reshape(1, -1, 1).to(dev)
+        cfg = g.make_cfg(R, C, grad_mode=args.grad_mode, precision=args.precision, shard=(mode == "sharded"))
+        hostpool.warm()                       # the worker processes exist before the first call, as in a driver
+        seq = list(warm[-min(2, len(warm)):]) + list(timed)
+        n_warm = len(seq) - len(timed)
+        barrier()
+        for pos, bi in enumerate(seq):
+            b = beams[bi]
+            Xh = torch.from_numpy(np.ascontiguousarray(b.X[None])).pin_memory()
+            yh = torch.from_numpy(np.ascontiguousarray(b.y)).reshape(1, -1, 1).pin_memory()
             hyps = [(-float(j), t) for j, t in enumerate(b.tokens)]
-            torch.cuda.synchronize()
+            vbfgs._COMPILED.clear()           # cold compile cache: every step compiles its 64 skeletons
+            flush.fill_(2)
+            barrier()
             t0 = time.perf_counter()
-            out = refine_hypotheses(hyps, Xd, yd, cfg, td, x0=b.x0)
+            out = refine_hypotheses(hyps, Xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True), cfg, td, x0=b.x0)
+            best = out["best_bfgs_preds"][0]  # the string a driver sympifies next (e.g. Feynman_test.py:78)
             torch.cuda.synchronize()
-            api_ms += (time.perf_counter() - t0) * 1e3
-            api_n += len(out["all_bfgs_preds"])
+            dt = (time.perf_counter() - t0) * 1e3
+            if rank == 0:
+                print(f"e2e_ms {b.name}:{dt:.1f} " + " ".join(f"{k}={v:.1f}" for k, v in vbfgs.LAST_TIMING.items()), file=sys.stderr)
+            if pos >= n_warm:
+                api_ms += dt
+                api_n += len(out["all_bfgs_loss"])
+                h2d = Xh.numel() * Xh.element_size() + yh.numel() * yh.element_size() + sum(x.nbytes for x in b.x0)
+                kmx = max(1, max(p.k for p in b.programs))   # scores + last points read back (records when sharded)
+                d2h = C * 8 * (4 + kmx) if mode == "sharded" else C * R * 8 * (1 + kmx)
+            del best
+
+    gc.enable()   # (off since the first timed loop: this process holds every beam's sympy trees, and a
+    #               generation-2 collection over them stalls a step for 50-100 ms; a driver holds one beam's)
 
     # ---- max over ranks ----
-    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, api_ms], dtype=torch.float64, device=dev)
     agg = torch.tensor([float(launches), flops, pevals, abytes, fit_ms, fit_n, score_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    total_ms_max, e2e_ms_max = t.tolist()
+    total_ms_max, api_ms_max = t.tolist()
     launches_all, flops_all, pevals_all, abytes_all, fit_ms_all, fit_n_all, score_ms_all = agg.tolist()
 
     if rank == 0:
@@ -484,29 +662,39 @@ def main():
         fp_peak = fp.get(key, derived)
         fp_src = "measured (profiles/fp_peaks.json)" if key in fp else f"derived: 148 SMs x lanes x 2 x {sm_max:.0f} MHz"
         cap = None
-        try:   # DRAM bytes of one launch of the dominant kernel, from the committed ncu capture
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_capture.json")))
-        except Exception:  # noqa: BLE001
-            pass
+        for name in ("r02_ncu_capture.json", "r01_ncu_capture.json"):
+            try:   # DRAM bytes of one launch of the dominant kernel, from the committed ncu capture
+                cap = json.load(open(os.path.join(ROOT, "profiles", name)))
+                break
+            except Exception:  # noqa: BLE001
+                pass
         traffic = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) if cap else None
         fit_s = fit_ms_all / 1e3 / world      # per-rank average kernel time
         n_launch = max(1.0, fit_n_all)
         achieved_tf = flops_all / world / max(fit_s, 1e-9) / 1e12
         achieved_gbs = abytes_all / world / max(fit_s, 1e-9) / 1e9
-        value = world * args.steps * C / (total_ms_max / 1e3)
+        n_steps_job = args.steps if mode == "sharded" else world * args.steps
+        value = n_steps_job * C / (total_ms_max / 1e3)
         line = {
             "metric": "candidate_fits_per_sec", "value": value, "unit": "candidate-fits/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong" if mode == "sharded" else "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
             "config": workload_config(args),
+            "partition": ("one beam's candidate x restart runs dealt over the ranks + one all-gather of per-candidate "
+                          "records per step (engine/sharding.py)") if mode == "sharded" else "whole beams per GPU",
             "point_evals_per_sec": pevals_all / (total_ms_max / 1e3),
-            "e2e": {"value": world * args.steps * C / (e2e_ms_max / 1e3), "unit": "candidate-fits/s",
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "path": "vsr_upload_points + vsr_upload_programs + vsr_fit_host (C ABI, host buffers)"},
-            "api_e2e": {"value": api_n / (api_ms / 1e3) if api_ms else None, "unit": "candidate-fits/s",
-                        "path": "refine_hypotheses(token ids, X, y, cfg, test_data): sympy compile (cold cache) + "
-                                "fit + prune + winner formatting, single process"},
+            "e2e": ({"value": n_steps_job * C / (api_ms_max / 1e3) if mode == "sharded" else world * api_n / (api_ms_max / 1e3),
+                     "unit": "candidate-fits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                     "path": "refine_hypotheses(token ids, pinned host X / y, cfg, test_data) -> dict: H2D copies, skeleton "
+                             "compilation (cold cache, host worker pool), fit (sharded over the ranks when N > 1), prune, "
+                             "winner formatting, D2H read", "host_workers": hostpool.default_workers()}
+                    if api_ms_max else None),
+            "e2e_abi": {"value": abi_n * C / (abi_ms / 1e3) if abi_ms else None, "unit": "candidate-fits/s",
+                        "h2d_bytes_per_step": int(h2d_abi), "d2h_bytes_per_step": int(d2h_abi), "n_gpus": 1,
+                        "path": "vsr_upload_points + vsr_upload_programs + vsr_fit_host (C ABI, host buffers, "
+                                "precompiled bytecode)"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {
@@ -520,16 +708,17 @@ def main():
                 "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                         "peak_source": hbm_src},
                 "note": "algorithmic flops per SURVEY 8d (1 per arithmetic node, transcendental = 1); the kernel "
-                        "is FP-pipe bound, not HBM bound: see profiles/ for ncu pipe utilisation"},
+                        "is issue / FP-pipe bound, not HBM bound: see profiles/ for ncu pipe utilisation"},
         }
+        if shard_check is not None:
+            line["sharded_check"] = shard_check
+        if replicas is not None:
+            line["replicas"] = replicas
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline([beams[bi] for bi in job], R, args.cpu_sample)
+            line["cpu_baseline"] = cpu_baseline([beams[bi] for bi in timed], args, args.cpu_seconds)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
-        if rank == 0:
-            import shutil
-            shutil.rmtree(claim_root, ignore_errors=True)
         dist.destroy_process_group()
 
 

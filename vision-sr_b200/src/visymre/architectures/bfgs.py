@@ -22,7 +22,7 @@ import sympy as sp
 import torch
 
 from ..dataset.generator import Generator
-from ..engine import fitter, isa
+from ..engine import fitter, hostpool, isa, sharding
 from ..engine.compiler import CompileError, compile_sympy
 from . import data
 
@@ -118,23 +118,144 @@ def _substitute_like_reference(expr_str, symbols, values):
 # same problem repeat most of their candidates (scripts/*_test.py loop 8x per equation)
 _COMPILED = {}
 _COMPILED_MAX = 8192
+# milliseconds the stages of the last _bfgs_batch call took on the host (measurement aid)
+LAST_TIMING = {}
 
 
-def _compile_candidate(toks, cfg, test_data, variables):
-    key = (tuple(int(t) for t in (toks.tolist() if hasattr(toks, "tolist") else toks)),
-           bool(_opt(cfg, "add_coefficients_if_not_existing", False)), tuple(variables),
-           test_data.id2word.get(3))
-    hit = _COMPILED.get(key)
-    if hit is None:
-        expr, k = skeleton_string(toks, cfg, test_data)
-        prog = compile_sympy(sp.sympify(expr), k, variables)
-        if len(_COMPILED) >= _COMPILED_MAX:
-            _COMPILED.pop(next(iter(_COMPILED)))
-        hit = _COMPILED[key] = (expr, k, prog)
+def compile_tokens(toks, cfg, test_data, variables):
+    """Q1-Q5 + lowering of ONE candidate: token ids -> (c-named infix string, k, Program)."""
+    expr, k = skeleton_string(toks, cfg, test_data)
+    return expr, k, compile_sympy(sp.sympify(expr), k, variables)
+
+
+def _cache_key(toks, cfg, test_data, variables):
+    return (tuple(int(t) for t in (toks.tolist() if hasattr(toks, "tolist") else toks)),
+            bool(_opt(cfg, "add_coefficients_if_not_existing", False)), tuple(variables),
+            test_data.id2word.get(3))
+
+
+def _remember(key, hit):
+    if len(_COMPILED) >= _COMPILED_MAX:
+        _COMPILED.pop(next(iter(_COMPILED)))
+    _COMPILED[key] = hit
     return hit
 
 
-def bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
+def _compile_candidate(toks, cfg, test_data, variables):
+    key = _cache_key(toks, cfg, test_data, variables)
+    hit = _COMPILED.get(key)
+    if hit is None:
+        hit = _remember(key, compile_tokens(toks, cfg, test_data, variables))
+    return hit
+
+
+def _host_workers(cfg):
+    n = _opt(cfg, "host_workers", None)
+    return hostpool.default_workers() if n is None else int(n)
+
+
+def _compile_candidates(pred_strs, cfg, test_data, variables):
+    """``(expr, k, Program)`` or the raised ``Exception`` for every candidate.  Cache misses are
+    compiled in the host pool, in chunks (sympy: 3-8 ms per candidate), when there are enough."""
+    keys = [_cache_key(t, cfg, test_data, variables) for t in pred_strs]
+    out = [_COMPILED.get(k) for k in keys]
+    miss = [i for i, h in enumerate(out) if h is None]
+    first = {}
+    for i in miss:                        # a beam may hold the same token sequence twice
+        first.setdefault(keys[i], i)
+    todo = sorted(first.values())
+    pool = hostpool.get_pool(_host_workers(cfg)) if len(todo) >= 8 else None
+    if pool is not None:
+        n = hostpool._POOL_N
+        chunks = [todo[j::n] for j in range(min(n, len(todo)))]
+        bits = (bool(_opt(cfg, "add_coefficients_if_not_existing", False)),)
+        id2word = dict(test_data.id2word)
+        jobs = [([[int(t) for t in (pred_strs[i].tolist() if hasattr(pred_strs[i], "tolist") else pred_strs[i])]
+                  for i in ch], bits, id2word, list(variables)) for ch in chunks]
+        for ch, res in zip(chunks, pool.map(hostpool.compile_chunk, jobs)):
+            for i, r in zip(ch, res):
+                out[i] = r if isinstance(r, Exception) else _remember(keys[i], r)
+    else:
+        for i in todo:
+            try:
+                out[i] = _remember(keys[i], compile_tokens(pred_strs[i], cfg, test_data, variables))
+            except Exception as exc:  # noqa: BLE001 -- the wrapper's contract (model.py:15-19)
+                out[i] = exc
+    for i in miss:
+        if out[i] is None:
+            out[i] = out[first[keys[i]]]
+    return out
+
+
+class LazyStr:
+    """``str(skeleton with the fitted constants in)``, produced when somebody reads it.  Printing a
+    fitted candidate through sympy costs 5-15 ms and every driver of the reference reads ONE string
+    per ``fitfunc`` call (``best_bfgs_preds[0]``, e.g. Feynman_test.py:78)."""
+    __slots__ = ("_job", "_text")
+
+    def __init__(self, job):
+        self._job, self._text = job, None
+
+    def __str__(self):
+        if self._text is None:
+            prog, _, syms, vals = self._job
+            self._text = str(_substitute(prog.expr, syms, vals))
+            self._job = None
+        return self._text
+
+    __repr__ = __str__
+
+
+class LazyStrings(list):
+    """A list of strings some of which are still ``LazyStr``: every way of reading an element
+    hands out (and keeps) the finished ``str``."""
+
+    def _get(self, i):
+        v = list.__getitem__(self, i)
+        if isinstance(v, LazyStr):
+            v = str(v)
+            list.__setitem__(self, i, v)
+        return v
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._get(j) for j in range(*i.indices(len(self)))]
+        return self._get(i if i >= 0 else i + len(self))
+
+    def __iter__(self):
+        return (self._get(i) for i in range(len(self)))
+
+    def __eq__(self, other):
+        return list(iter(self)) == list(other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        return repr(list(iter(self)))
+
+    def __reduce__(self):
+        return (list, (list(iter(self)),))
+
+
+def _format_all(jobs, cfg):
+    """``str(skeleton with the numbers in)`` for every job ``(Program, skeleton string, symbols,
+    values)`` -- in the host pool when there are enough of them."""
+    pool = hostpool.get_pool(_host_workers(cfg)) if len(jobs) >= 8 else None
+    if pool is None:
+        return [str(_substitute(prog.expr, syms, vals)) for prog, _, syms, vals in jobs]
+    n = hostpool._POOL_N
+    idx = [list(range(j, len(jobs), n)) for j in range(min(n, len(jobs)))]
+    payload = [[(jobs[i][1], [sy.name for sy in jobs[i][2]], [float(v) for v in jobs[i][3]]) for i in ch] for ch in idx]
+    out = [None] * len(jobs)
+    for ch, res in zip(idx, pool.map(hostpool.format_chunk, payload)):
+        for i, r in zip(ch, res):
+            if isinstance(r, Exception):   # not expected: redo it here, where the error belongs
+                r = str(_substitute(jobs[i][0].expr, jobs[i][2], jobs[i][3]))
+            out[i] = r
+    return out
+
+
+def bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_strings=False):
     """Fit every candidate of a beam in one go (see ``_bfgs_batch``).
 
     With ``cfg.bfgs.collapse_duplicates`` (off by default) candidates that
@@ -146,7 +267,7 @@ def bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
     """
     pred_strs = list(pred_strs)
     if not _opt(cfg, "collapse_duplicates", False) or len(pred_strs) < 2:
-        return _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=x0, engine=engine)
+        return _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=x0, engine=engine, lazy_strings=lazy_strings)
     variables = list(test_data.total_variables)
     first, rep_of, own_expr = {}, [], []
     for i, toks in enumerate(pred_strs):
@@ -160,7 +281,7 @@ def bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
     reps = sorted(set(rep_of))
     pos = {r: j for j, r in enumerate(reps)}
     sub = _bfgs_batch([pred_strs[r] for r in reps], X, y, cfg, test_data,
-                      x0=None if x0 is None else [x0[r] for r in reps], engine=engine)
+                      x0=None if x0 is None else [x0[r] for r in reps], engine=engine, lazy_strings=lazy_strings)
     out = []
     for i, r in enumerate(rep_of):
         res = sub[pos[r]]
@@ -170,15 +291,24 @@ def bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
     return out
 
 
-def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
+def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_strings=False):
     """Fit every candidate of a beam in one go.
 
     Returns a list with one entry per candidate: the reference's 4-tuple
     ``(best_expr_str, best_consts, best_loss, expr)`` or the ``Exception`` that
     ``bfgs()`` would have raised for it.  ``x0``: optional list (one per candidate) of
     ``[R, k]`` starting points; default is the reference's ``np.random.randn(k) * 10``
-    per restart (bfgs.py:103).
+    per restart (bfgs.py:103).  ``lazy_strings``: ``best_expr_str`` of every candidate is a
+    ``LazyStr`` (printed through sympy when read) instead of a ``str``.
     """
+    import time as _time
+    _t = [_time.perf_counter()]
+
+    def _mark(name):
+        now = _time.perf_counter()
+        LAST_TIMING[name] = LAST_TIMING.get(name, 0.0) + (now - _t[0]) * 1e3
+        _t[0] = now
+    LAST_TIMING.clear()
     y = y.squeeze()
     Xt = torch.as_tensor(X)
     if Xt.dim() == 2:
@@ -189,15 +319,16 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
 
     # ---- Q1-Q5 + compilation, per candidate (failures stay per candidate) ----
     cands = []
-    for toks in pred_strs:
+    for hit in _compile_candidates(pred_strs, cfg, test_data, variables):
         c = _Candidate()
-        try:
-            c.expr, c.k, c.prog = _compile_candidate(toks, cfg, test_data, variables)
-        except Exception as exc:  # noqa: BLE001 -- the wrapper's contract (model.py:15-19)
-            c.error = exc
+        if isinstance(hit, Exception):
+            c.error = hit
+        else:
+            c.expr, c.k, c.prog = hit
         cands.append(c)
     live = [i for i, c in enumerate(cands) if c.error is None]
     results = [c.error for c in cands]
+    _mark("compile")
     if not live:
         return results
 
@@ -229,6 +360,7 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
     eng.set_points(Xt[0], yt_fit, dtypes=tuple({eval_dtype, score_dtype, fitter.F64}))
     eng.set_programs([cands[i].prog for i in live])
     opts = _engine_opts(cfg, scale, eval_dtype, score_dtype)
+    _mark("upload")
 
     # ---- Q8 restarts: one run per (candidate, restart) ----
     kmax = max(1, max(cands[i].k for i in live))
@@ -244,14 +376,27 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
             start[li * R + r, :k] = v
             run_prog.append(li)
             run_slot.append(li * R + r)
-    res = eng.fit(run_prog, run_slot, torch.from_numpy(start), opts)
-    lastx = res.lastx.cpu().numpy()
-    final = res.final_mse.cpu().numpy()
-    if score_dtype == fitter.F32:
-        final = final.astype(np.float32)
-    if rows_removed:
-        final = np.full_like(final, 1e9)  # y_found - y raises on the shape mismatch (bfgs.py:130-131)
+    world = sharding.world_size() if _opt(cfg, "shard", True) and not rows_removed else 1
+    if world > 1:
+        # the (candidate, restart) runs of the beam are dealt over the ranks of the default
+        # process group, every rank fits its share, ONE all-gather brings back a record per candidate
+        # (score, restart, constants) and every rank takes the same argmin.  Every rank must have
+        # been called with the same candidates and points; the starting points are rank 0's.
+        start_dev = sharding.broadcast_from_rank0(torch.from_numpy(start).to(eng.device))
+        cost = np.repeat([(cands[ci].k + 1.0) * cands[ci].prog.n_insns for ci in live], R)
+        win, _ = sharding.fit_sharded(eng, [cands[ci].k for ci in live], R, start_dev, opts, cost=cost,
+                                      key_dtype=torch.float32 if score_dtype == fitter.F32 else None)
+        win = win.cpu().numpy()
+    else:
+        res = eng.fit(run_prog, run_slot, torch.from_numpy(start), opts)
+        lastx = res.lastx.cpu().numpy()
+        final = res.final_mse.cpu().numpy()
+        if score_dtype == fitter.F32:
+            final = final.astype(np.float32)
+        if rows_removed:
+            final = np.full_like(final, 1e9)  # y_found - y raises on the shape mismatch (bfgs.py:130-131)
 
+    _mark("fit")
     # ---- Q10/Q11 pick the restart, Q12 collect prune work ----
     thr = _opt(cfg, "prune_threshold", 1e-3)
     tol = _opt(cfg, "prune_tolerance", 1.05)
@@ -259,13 +404,17 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
     prune_jobs = []
     for li, ci in enumerate(live):
         c = cands[ci]
-        F_loss = final[li * R:(li + 1) * R]
-        try:
-            k_best = int(np.nanargmin(F_loss))
-        except ValueError:
-            k_best = 0
-        best_consts = lastx[li * R + k_best, :c.k].copy()
-        best_loss = F_loss[k_best]
+        if world > 1:
+            best_consts = win[li, 3:3 + c.k].copy()
+            best_loss = np.float32(win[li, -1]) if score_dtype == fitter.F32 else win[li, -1]
+        else:
+            F_loss = final[li * R:(li + 1) * R]
+            try:
+                k_best = int(np.nanargmin(F_loss))
+            except ValueError:
+                k_best = 0
+            best_consts = lastx[li * R + k_best, :c.k].copy()
+            best_loss = F_loss[k_best]
         csyms = [sp.Symbol(f"c{i}") for i in range(c.k)]
         picked[ci] = [best_consts, best_loss, csyms]
         if c.k > 0:
@@ -328,7 +477,9 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
         if ok:
             picked[j["ci"]] = [vals, pruned_loss, csyms, True, j["zero"]]
 
+    _mark("prune")
     # ---- Q13 strings ----
+    fmt_jobs, fmt_meta = [], []
     for ci in live:
         c = cands[ci]
         entry = picked[ci]
@@ -339,12 +490,16 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None):
         if len(entry) > 3:  # pruned: zeros first, then the re-fitted ones (bfgs.py:184-196)
             order = list(entry[4]) + [i for i in range(c.k) if i not in entry[4]]
             vals = [0.0 if i in entry[4] else best_consts[i] for i in order]
-            final_expr = _substitute(c.prog.expr, [csyms[i] for i in order], vals)
+            fmt_jobs.append((c.prog, c.expr, [csyms[i] for i in order], vals))
             consts_out = [0.0 if i in entry[4] else best_consts[i] for i in range(c.k)]
         else:
-            final_expr = _substitute(c.prog.expr, csyms, list(best_consts))
+            fmt_jobs.append((c.prog, c.expr, csyms, list(best_consts)))
             consts_out = best_consts
-        results[ci] = (str(final_expr), consts_out, best_loss, c.expr)
+        fmt_meta.append((ci, consts_out, best_loss))
+    texts = [LazyStr(j) for j in fmt_jobs] if lazy_strings else _format_all(fmt_jobs, cfg)
+    for (ci, consts_out, best_loss), text in zip(fmt_meta, texts):
+        results[ci] = (text, consts_out, best_loss, cands[ci].expr)
+    _mark("strings")
     return results
 
 

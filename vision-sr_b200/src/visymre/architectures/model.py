@@ -12,7 +12,7 @@ decoder forward and the beam loop above line 444 stay the reference's PyTorch co
 import numpy as np
 import torch
 
-from .bfgs import bfgs, bfgs_batch
+from .bfgs import LazyStrings, bfgs, bfgs_batch
 
 UNARY_NAMES = ("abs", "asin", "cos", "exp", "ln", "sin", "sqrt", "tan")   # model.py:295
 BINARY_NAMES = ("add", "div", "mul", "pow", "sub")                        # model.py:296
@@ -107,13 +107,14 @@ def refine_hypotheses(hyps, X, y, cfg_params, test_data, x0=None, engine=None):
     P_bfgs, L_bfgs, token = [], [], []
     if valid:
         try:
-            outs = bfgs_batch(valid, X, y, cfg_params, test_data, x0=x0, engine=engine)
+            outs = bfgs_batch(valid, X, y, cfg_params, test_data, x0=x0, engine=engine, lazy_strings=True)
         except Exception as exc:  # noqa: BLE001 -- a batch-level failure fails every candidate
             outs = [exc] * len(valid)
+        P_bfgs = LazyStrings()   # every string the reference returns; printed when read
         for ww, out in zip(valid, outs):
             if isinstance(out, Exception):
                 continue
-            P_bfgs.append(str(out[0]))
+            P_bfgs.append(out[0])
             L_bfgs.append(out[2])
             token.append(ww)
 

@@ -25,7 +25,19 @@ def partition_runs(cost, world):
     return [np.sort(order[r::world]) for r in range(world)]
 
 
-def local_best_records(final_mse, loss, consts, n_cand, n_restarts, mine):
+def world_size(group=None):
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def broadcast_from_rank0(t, group=None):
+    """Rank 0's copy of ``t`` on every rank (starting points drawn from an unseeded RNG differ
+    per process, bfgs.py:103)."""
+    if world_size(group) > 1:
+        dist.broadcast(t, src=0, group=group)
+    return t
+
+
+def local_best_records(final_mse, loss, consts, n_cand, n_restarts, mine, key_dtype=None):
     """Per-candidate best of THIS rank's restarts.
 
     final_mse, loss: [C*R]; consts: [C*R, kmax]; mine: bool [C*R], runs this rank fitted.
@@ -37,6 +49,8 @@ def local_best_records(final_mse, loss, consts, n_cand, n_restarts, mine):
     C, R = n_cand, n_restarts
     kmax = consts.shape[1]
     fm = final_mse.reshape(C, R).to(torch.float64)
+    if key_dtype is not None:   # the reference compares the scores in X's dtype (bfgs.py:126-141)
+        fm = fm.to(key_dtype).to(torch.float64)
     own = mine.reshape(C, R)
     ridx = torch.arange(R, device=dev).expand(C, R)
     key = torch.where(own & ~torch.isnan(fm), fm, torch.full_like(fm, float("inf")))
@@ -93,7 +107,7 @@ def empty_result(n_slots, kstride, device):
                      info=torch.full((n_slots, 4), -1, dtype=torch.int32, device=device))
 
 
-def fit_sharded(engine, programs_k, n_restarts, x0, opts, cost=None, group=None):
+def fit_sharded(engine, programs_k, n_restarts, x0, opts, cost=None, group=None, key_dtype=None):
     """Fit a beam with its runs sharded over the ranks of ``group``.
 
     programs_k: constants per candidate (engine.set_programs was called with the same
@@ -117,5 +131,5 @@ def fit_sharded(engine, programs_k, n_restarts, x0, opts, cost=None, group=None)
         res = empty_result(C * R, int(torch.as_tensor(x0).shape[1]), engine.device)
     mine = torch.zeros(C * R, dtype=torch.bool, device=res.loss.device)
     mine[torch.as_tensor(mine_idx, device=mine.device)] = True
-    rec = local_best_records(res.final_mse, res.loss, res.lastx, C, R, mine)
+    rec = local_best_records(res.final_mse, res.loss, res.lastx, C, R, mine, key_dtype)
     return allgather_best(rec, group), res

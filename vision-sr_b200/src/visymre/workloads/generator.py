@@ -262,19 +262,23 @@ def feynman_beams(n_points=10_000, n_cand=64, n_restarts=10, limit=None, bonus=F
     return beams, td
 
 
+def low_beam(e, row, n_points, n_cand, n_restarts, td):
+    """One low_benchmarks.csv row -> beam (the table gives one range for all variables)."""
+    variables = [dict(low=row["range"][0], high=row["range"][1]) for _ in range(max(1, row["n_vars"]))]
+    nv = max([int(s.name.split("_")[1]) for s in sp.sympify(row["formula"], locals=dict(_SYM_LOCALS)).free_symbols
+              if s.name.startswith("x_")] + [1])
+    while len(variables) < nv:
+        variables.append(dict(variables[0]))
+    return build_beam(10_000 + e, row["name"], row["formula"], variables, n_points, n_cand, n_restarts, td)
+
+
 def low_beams(n_points=500, n_cand=16, n_restarts=10, limit=None):
     """BASELINE config 1: low_benchmarks.csv rows (Nguyen-style, 1-2 variables)."""
     t = load_tables()
     td = make_test_data(t)
     beams = []
     for e, row in enumerate(t["low"]):
-        variables = [dict(low=row["range"][0], high=row["range"][1]) for _ in range(max(1, row["n_vars"]))]
-        nv = max([int(s.name.split("_")[1]) for s in sp.sympify(row["formula"], locals=dict(_SYM_LOCALS)).free_symbols
-                  if s.name.startswith("x_")] + [1])
-        while len(variables) < nv:
-            variables.append(dict(variables[0]))
-        b = build_beam(10_000 + e, row["name"], row["formula"], variables, n_points, n_cand,
-                       n_restarts, td)
+        b = low_beam(e, row, n_points, n_cand, n_restarts, td)
         if b is not None:
             beams.append(b)
         if limit and len(beams) >= limit:
