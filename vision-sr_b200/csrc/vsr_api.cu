@@ -106,6 +106,7 @@ struct vsr_handle {
   int64_t launches = 0;
   int hook[4] = {0, 0, 0, 0};  // VSR_GEOMETRY measurement hook, read once in vsr_create
   int steal_span = 3;          // a launch takes runs of groups up to this many tangent widths narrower
+  int latency_k = 0;
   // measurement hooks
   bool profiling = false;
   long long* phase_cycles = nullptr;  // optional device buffer [n_slots][8], see vsr_set_phase_buffer
@@ -419,6 +420,7 @@ int vsr_create(int device, vsr_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   if (const char* env = getenv("VSR_GEOMETRY")) sscanf(env, "%d:%d:%d:%d", &h->hook[0], &h->hook[1], &h->hook[2], &h->hook[3]);
   if (const char* env = getenv("VSR_STEAL_SPAN")) h->steal_span = atoi(env);
+  if (const char* env = getenv("VSR_LATENCY_K")) h->latency_k = atoi(env);
   // scratch every fit needs, allocated here rather than inside the first fit: run lists (pinned
   // + device), run counters, eval partials, the side streams and their events
   e = h->h_lists.reserve(256 << 10);
@@ -915,6 +917,8 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     const int P = points_per_thread(g.K);
     int cap = opts->eval_dtype == VSR_F64 ? fit_threads_cap<double>(g.K) : fit_threads_cap<float>(g.K);
     if (hook_threads > 0) cap = std::min(cap, std::max(32, hook_threads & ~31));
+    // experiment hook: VSR_LATENCY_K=k -- groups of width >= k use 16 half-width CTAs per cluster
+    if (h->latency_k > 0 && g.K >= h->latency_k && hook_threads <= 0) cap = std::min(cap, 320);
     const int max_cluster = hook_cluster > 0 ? std::min(hook_cluster, kMaxCluster) : kMaxCluster;
     int n_cols = 0;
     for (int j = 0; j < VSR_MAX_VARS; ++j) a.col_of_var[j] = ((all_vars >> j) & 1u) ? n_cols++ : -1;

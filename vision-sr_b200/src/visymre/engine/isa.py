@@ -8,7 +8,18 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-CSRC_DIR = os.path.normpath(os.path.join(_HERE, "..", "..", "..", "csrc"))
+
+
+def _find_csrc():
+    """Where libvsr.so and vsr_isa.h live: $VSR_CSRC, the repo's csrc/ (three levels up), or the
+    ``_native`` directory ``overlay.py`` puts beside this file in a reference checkout."""
+    for d in (os.environ.get("VSR_CSRC"), os.path.join(_HERE, "..", "..", "..", "csrc"), os.path.join(_HERE, "_native")):
+        if d and os.path.exists(os.path.join(d, "vsr_isa.h")):
+            return os.path.normpath(d)
+    return os.path.normpath(os.path.join(_HERE, "..", "..", "..", "csrc"))
+
+
+CSRC_DIR = _find_csrc()
 ISA_HEADER = os.path.join(CSRC_DIR, "vsr_isa.h")
 
 

@@ -21,7 +21,7 @@ import sympy as sp
 
 from ..architectures import data as tok
 from ..architectures.bfgs import skeleton_string
-from ..architectures.model import BINARY_NAMES, UNARY_NAMES, analyze_prefix_tree_context
+from ..architectures.refine import BINARY_NAMES, UNARY_NAMES, analyze_prefix_tree_context
 from ..dataset.generator import Generator
 from ..engine.compiler import CompileError, compile_sympy
 
