@@ -6,6 +6,7 @@ import sympy as sp
 
 from src.visymre import hlsc, scoring
 from src.visymre.architectures import model as vmodel
+from src.visymre.architectures import refine as vrefine
 from src.visymre.engine import isa
 
 
@@ -45,10 +46,10 @@ def test_restarts_context_restores_the_knob():
 
 
 def test_beam_mask_token_sets():
-    assert vmodel._bits([0, 3, 63]) == (1 << 0) | (1 << 3) | (1 << 63)
-    assert vmodel._bits(None) == 0
+    assert vrefine._bits([0, 3, 63]) == (1 << 0) | (1 << 3) | (1 << 63)
+    assert vrefine._bits(None) == 0
     with pytest.raises(ValueError):
-        vmodel._bits([64])
+        vrefine._bits([64])
     # the ctypes mirror of vsr_beam_rules has the header's layout: 5 x u64 + 6 x i32
     from src.visymre.engine import native
     import ctypes
