@@ -105,3 +105,40 @@ def test_workload_is_seeded_and_well_formed(beams):
         assert len(set(map(tuple, b.tokens))) == len(b.tokens) == 24
         progs = wg.compile_beam(b, td)
         assert all(p.k == x.shape[1] and p.k <= 8 for p, x in zip(progs, b.x0))
+
+
+def test_parse_skeleton_builds_sympifys_tree(beams, golden):
+    """engine/compiler.py:parse_skeleton against sympy.sympify (what the reference calls, bfgs.py:81)
+    on every skeleton string of the workload beams, the golden cases and the odd words of the
+    vocabulary; strings outside the closed vocabulary fall through to sympify."""
+    import pickle
+    from src.visymre.engine.compiler import compile_skeleton, parse_skeleton
+    bs, td = beams
+    cfg = wg.make_cfg(3)
+    texts = [vbfgs.skeleton_string(ids, cfg, td)[0] for b in bs for ids in b.tokens]
+    texts += [c["skeleton"] for c in golden["cases"] if c.get("skeleton")]
+    texts += ["(1/((x_1)**2))", "((pi)*((x_2)**3))+((1)/(2))", "((E)**(c0))-((3)/(x_1))", "(atan((c0)*(I)))",
+              "((x_1)-(x_1))", "((2)*(3))", "(ln(Abs((c0)+(-1))))", "(((x_1)**5)/((-2)+(c1)))"]
+    assert len(texts) > 100
+    for t in texts:
+        assert sp.srepr(parse_skeleton(t)) == sp.srepr(sp.sympify(t)), t
+    assert parse_skeleton("x_1 + foo(2)") == sp.sympify("x_1 + foo(2)")      # unknown word: sympify's answer
+    assert parse_skeleton("2.5*x_1") == sp.sympify("2.5*x_1")                # a float literal: sympify's answer
+    with pytest.raises(Exception):
+        parse_skeleton("((x_1)+")
+    # a program that crosses a process boundary leaves its tree behind and parses its source again
+    prog = compile_skeleton("((c0)*(sin((x_1)+(c1))))", 2, td.total_variables)
+    back = pickle.loads(pickle.dumps(prog))
+    assert back._expr is None and sp.srepr(back.expr) == sp.srepr(prog.expr)
+    assert np.array_equal(back.insns, prog.insns) and back.k == 2
+
+
+def test_derivative_is_constant_shortcut_agrees_with_sympy():
+    """bfgs.py:160 ``diff(expr, c).is_constant()``: the numeric shortcut may only ever answer what
+    sympy answers."""
+    c0 = sp.Symbol("c0")
+    for text in ["(c0)*((x_1)+(x_2))", "(c0)*(sin(x_1)**2+cos(x_1)**2)", "(c0)+(x_1)", "(c0)*(c0)*(x_1)", "sin(c0)",
+                 "(c0)*(3)", "(c0)/(x_1)", "(c0)*(((x_1)+1)**2-(x_1)**2-2*(x_1))", "exp((c0)*(x_1))",
+                 "(c0)*(tan(cos((x_1)*(x_3)))+((x_2)*(x_4)))/((x_1)+(x_2))"]:
+        e = sp.sympify(text)
+        assert bool(vbfgs._derivative_is_constant(e, c0)) == bool(sp.diff(e, c0).is_constant()), text

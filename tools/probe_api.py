@@ -8,7 +8,7 @@ from src.visymre.architectures import bfgs as vb
 from src.visymre.architectures.model import refine_hypotheses
 from src.visymre.engine import hostpool
 from src.visymre.workloads import generator as g
-beams = bench.make_workload(8, 10_000, 64, 10)
+beams = bench.make_workload(int(os.environ.get("NB", "8")), 10_000, 64, 10)
 td = g.make_test_data(); cfg = g.make_cfg(10, 64)
 dev = torch.device("cuda:0")
 print("workers", hostpool.warm())

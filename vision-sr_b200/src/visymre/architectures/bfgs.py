@@ -23,7 +23,7 @@ import torch
 
 from ..dataset.generator import Generator
 from ..engine import fitter, hostpool, isa, sharding
-from ..engine.compiler import CompileError, compile_sympy
+from ..engine.compiler import CompileError, compile_sympy, parse_skeleton
 from . import data
 
 
@@ -114,6 +114,71 @@ def _substitute_like_reference(expr_str, symbols, values):
     return final
 
 
+def prepare_prune(prog, small, variables):
+    """Symbolic half of Q12 (bfgs.py:156-178) for one candidate whose best constants ``small`` are
+    below the threshold: ``(zero_idx, rest, pruned Program | None, constant-free Program | Exception
+    | None)``, or None when nothing is pruned (or the pruned skeleton cannot be lowered: the unpruned
+    fit stays)."""
+    csyms = [sp.Symbol(f"c{i}") for i in range(prog.k)]
+    zero_idx = []
+    for i in small:
+        if prog.k == 1 and not _derivative_is_constant(prog.expr, csyms[i]):
+            continue
+        zero_idx.append(i)
+    if not zero_idx:
+        return None
+    rest = [i for i in range(prog.k) if i not in zero_idx]
+    if rest:
+        pruned = prog.expr.subs({csyms[i]: 0.0 for i in zero_idx})
+        pruned = pruned.xreplace({csyms[i]: sp.Symbol(f"c{j}") for j, i in enumerate(rest)})
+        try:
+            out = compile_sympy(pruned, len(rest), variables)
+        except CompileError:
+            return None
+        out._expr = None           # nobody reads the pruned tree again
+        return zero_idx, rest, out, None
+    try:   # every constant pruned: the constant-free expression is scored as it is
+        zprog = compile_sympy(prog.expr.subs({s: 0.0 for s in csyms}), 0, variables)
+        zprog._expr = None
+    except Exception as exc:  # noqa: BLE001 -- a singular tree (zoo*x_1 ...), scored 1e9 by the caller
+        zprog = hostpool._portable(exc)
+    return zero_idx, rest, None, zprog
+
+
+def _prepare_prunes(items, variables, cfg):
+    pool = hostpool.get_pool(_host_workers(cfg)) if len(items) >= 4 else None
+    if pool is None:
+        return [prepare_prune(prog, small, variables) for prog, small in items]
+    jobs = [(prog, small, list(variables)) for prog, small in items]
+    return list(pool.map(hostpool.prune_task, jobs))
+
+
+def _derivative_is_constant(expr, sym):
+    """``sp.diff(expr, sym).is_constant()`` (bfgs.py:160), without its cost where the answer is plain.
+
+    ``is_constant`` simplifies the derivative and then probes it numerically (25-160 ms on the
+    workload's skeletons).  For a derivative that takes two clearly different finite values at two
+    points it can only answer False: simplification keeps the function, so either its own numeric
+    probes differ or some partial derivative is not identically zero, and both paths return False
+    (sympy/core/expr.py:is_constant).  Everything else -- no free symbols, equal or non-finite
+    probes -- is left to sympy itself."""
+    d = sp.diff(expr, sym)
+    free = sorted(d.free_symbols, key=lambda q: q.name)
+    if free:
+        try:
+            vals = []
+            for point in (0.3779, 1.6180, -0.7321):
+                v = complex(d.evalf(17, subs={q: point + 0.0917 * j for j, q in enumerate(free)}))
+                if v == v and abs(v) != float("inf"):
+                    vals.append(v)
+            for a in vals[1:]:
+                if abs(a - vals[0]) > 1e-6 * max(1.0, abs(a), abs(vals[0])):
+                    return False
+        except Exception:  # noqa: BLE001 -- whatever went wrong, sympy decides
+            pass
+    return d.is_constant()
+
+
 # compiled skeletons, keyed by the token sequence: beams of successive fitfunc calls on the
 # same problem repeat most of their candidates (scripts/*_test.py loop 8x per equation)
 _COMPILED = {}
@@ -125,7 +190,9 @@ LAST_TIMING = {}
 def compile_tokens(toks, cfg, test_data, variables):
     """Q1-Q5 + lowering of ONE candidate: token ids -> (c-named infix string, k, Program)."""
     expr, k = skeleton_string(toks, cfg, test_data)
-    return expr, k, compile_sympy(sp.sympify(expr), k, variables)
+    prog = compile_sympy(parse_skeleton(expr), k, variables)
+    prog.source = expr          # lets the program cross a process boundary without its sympy tree
+    return expr, k, prog
 
 
 def _cache_key(toks, cfg, test_data, variables):
@@ -166,12 +233,13 @@ def _compile_candidates(pred_strs, cfg, test_data, variables):
     todo = sorted(first.values())
     pool = hostpool.get_pool(_host_workers(cfg)) if len(todo) >= 8 else None
     if pool is not None:
-        n = hostpool._POOL_N
-        chunks = [todo[j::n] for j in range(min(n, len(todo)))]
+        # small tasks, longest skeletons first: the workers stay evenly loaded to the end
+        todo.sort(key=lambda i: -len(keys[i][0]))
+        per = max(1, min(4, len(todo) // (3 * hostpool._POOL_N)))
+        chunks = [todo[j:j + per] for j in range(0, len(todo), per)]
         bits = (bool(_opt(cfg, "add_coefficients_if_not_existing", False)),)
         id2word = dict(test_data.id2word)
-        jobs = [([[int(t) for t in (pred_strs[i].tolist() if hasattr(pred_strs[i], "tolist") else pred_strs[i])]
-                  for i in ch], bits, id2word, list(variables)) for ch in chunks]
+        jobs = [([list(keys[i][0]) for i in ch], bits, id2word, list(variables)) for ch in chunks]
         for ch, res in zip(chunks, pool.map(hostpool.compile_chunk, jobs)):
             for i, r in zip(ch, res):
                 out[i] = r if isinstance(r, Exception) else _remember(keys[i], r)
@@ -401,7 +469,7 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
     thr = _opt(cfg, "prune_threshold", 1e-3)
     tol = _opt(cfg, "prune_tolerance", 1.05)
     picked = {}
-    prune_jobs = []
+    prune_jobs, prune_todo = [], []
     for li, ci in enumerate(live):
         c = cands[ci]
         if world > 1:
@@ -417,26 +485,18 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
             best_loss = F_loss[k_best]
         csyms = [sp.Symbol(f"c{i}") for i in range(c.k)]
         picked[ci] = [best_consts, best_loss, csyms]
-        if c.k > 0:
-            zero_idx = []
-            for i, v in enumerate(best_consts):
-                if abs(v) < thr:
-                    if c.k == 1 and not sp.diff(c.expr, csyms[i]).is_constant():
-                        continue
-                    zero_idx.append(i)
-            if zero_idx:
-                rest = [i for i in range(c.k) if i not in zero_idx]
-                job = dict(ci=ci, zero=zero_idx, rest=rest, prog=None)
-                if rest:
-                    pruned = c.prog.expr.subs({csyms[i]: 0.0 for i in zero_idx})
-                    pruned = pruned.xreplace({csyms[i]: sp.Symbol(f"c{j}") for j, i in enumerate(rest)})
-                    try:
-                        job["prog"] = compile_sympy(pruned, len(rest), variables)
-                    except CompileError:
-                        job = None  # pruned loss cannot be evaluated: keep the unpruned fit
-                if job is not None:
-                    prune_jobs.append(job)
+        small = [i for i, v in enumerate(best_consts) if abs(v) < thr] if c.k > 0 else []
+        if small:
+            prune_todo.append((ci, small))
+    # the symbolic half of Q12 (derivative test, substitution of the zeros, lowering of the pruned
+    # skeleton) is independent per candidate: in the host pool when there are enough of them
+    prepared = _prepare_prunes([(cands[ci].prog, small) for ci, small in prune_todo], variables, cfg)
+    for (ci, small), got in zip(prune_todo, prepared):
+        if got is not None:
+            zero_idx, rest, prog, zprog = got
+            prune_jobs.append(dict(ci=ci, zero=zero_idx, rest=rest, prog=prog, zprog=zprog))
 
+    _mark("prune_sym")
     # ---- Q12 re-fit the pruned skeletons (one more BFGS each, from the best point) ----
     fit_jobs = [j for j in prune_jobs if j["prog"] is not None]
     if fit_jobs:
@@ -451,6 +511,7 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
         ploss, _ = eng.eval(list(range(len(fit_jobs))), pres.consts, dtype=score_dtype)
         pconsts = pres.consts.cpu().numpy()
         ploss = ploss.cpu().numpy()
+        _mark("prune_fit")
         for ji, j in enumerate(fit_jobs):
             j["x"] = pconsts[ji, :len(j["rest"])]
             j["loss"] = ploss[ji]
@@ -463,8 +524,9 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
             pruned_loss = j["loss"]
         else:  # every constant pruned: evaluate the constant-free expression
             try:
-                zprog = compile_sympy(c.prog.expr.subs({s: 0.0 for s in csyms}), 0, variables)
-                eng.set_programs([zprog])
+                if isinstance(j["zprog"], Exception):
+                    raise j["zprog"]
+                eng.set_programs([j["zprog"]])
                 zl, _ = eng.eval([0], torch.zeros((1, 1)), dtype=score_dtype)
                 pruned_loss = float(zl.cpu().numpy()[0])
             except Exception:  # noqa: BLE001 -- a singular tree (zoo*x_1 ...): bfgs.py:196-202 scores it 1e9,

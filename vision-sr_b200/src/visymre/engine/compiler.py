@@ -17,6 +17,7 @@ Children of binary nodes are ordered Sethi-Ullman style and leaf operands are fo
 into the instruction, so the operand stack is only touched when both children of a
 node are non-trivial.
 """
+import re
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -40,7 +41,23 @@ class Program:
     n_nodes: int                 # sympy nodes lowered (program "length" L)
     flops: int                   # algorithmic flops per point-eval (SURVEY 8d weights)
     sfu: int = 0                 # transcendental nodes per point-eval
-    expr: object = field(default=None, repr=False)  # the sympy expression
+    _expr: object = field(default=None, repr=False)   # the sympy expression (see ``expr``)
+    source: str = None           # the infix string it was parsed from, when there is one
+
+    @property
+    def expr(self):
+        """The sympy tree the program was lowered from.  A program that crossed a process boundary
+        carries only its ``source`` string (pickled sympy trees cost more than the bytecode) and
+        parses it again when the tree is first needed (prune, winner formatting)."""
+        if self._expr is None and self.source is not None:
+            self._expr = parse_skeleton(self.source)
+        return self._expr
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        if d.get("source") is not None:
+            d["_expr"] = None
+        return d
 
     @property
     def n_insns(self):
@@ -48,6 +65,41 @@ class Program:
 
     def disassemble(self):
         return isa.disassemble(self.insns, self.imms)
+
+
+# ---- infix string -> sympy tree ----------------------------------------------------------------------
+# The reference hands the c-named infix string to ``sympify`` (bfgs.py:81): tokenizer, four token
+# transformations, ``eval``.  The strings of this path are fully parenthesised expressions over a
+# closed vocabulary (dataset/generator.py:_TEMPLATES), so evaluating them directly with the same names
+# bound and integer literals wrapped in ``Integer`` builds the same tree through the same operator
+# calls (tests/test_host_path.py compares ``srepr`` on the workloads) at ~3/4 of the cost; anything
+# outside that vocabulary goes through ``sympify``.
+_PARSE_NAMES = {n: getattr(sp, n) for n in ("sin", "cos", "tan", "exp", "sqrt", "Abs", "asin", "atan", "acos",
+                                            "sinh", "cosh", "tanh", "log", "pi", "E", "I", "Integer")}
+_PARSE_NAMES["ln"] = sp.log
+_PARSE_INT = re.compile(r"(?<![\w.])(\d+)(?![\w.])")
+_PARSE_WORD = re.compile(r"[A-Za-z_]\w*")
+_PARSE_SYMBOL = re.compile(r"(?:x_|c)\d+\Z")
+_PARSE_SAFE = re.compile(r"[\w\s()+\-*/]*\Z")
+_SYMBOLS = {}
+
+
+def parse_skeleton(text):
+    """``sympy.sympify(text)`` for the skeleton strings of this path (same tree, less overhead)."""
+    if not isinstance(text, str) or not _PARSE_SAFE.match(text):
+        return sp.sympify(text)
+    ns = {"__builtins__": {}}
+    for w in set(_PARSE_WORD.findall(text)):
+        if w in _PARSE_NAMES:
+            ns[w] = _PARSE_NAMES[w]
+        elif _PARSE_SYMBOL.match(w):
+            ns[w] = _SYMBOLS.get(w) or _SYMBOLS.setdefault(w, sp.Symbol(w))
+        else:
+            return sp.sympify(text)
+    try:
+        return eval(_PARSE_INT.sub(r"Integer(\1)", text), ns)   # noqa: S307 -- closed vocabulary, no builtins
+    except Exception:  # noqa: BLE001 -- let sympify raise what the reference would see
+        return sp.sympify(text)
 
 
 _UNARY = {
@@ -368,9 +420,11 @@ def compile_sympy(expr, k, variables):
         insns=np.asarray(low.code, dtype=np.uint64),
         imms=np.asarray(low.imms if low.imms else [0.0], dtype=np.float64),
         k=k, var_mask=low.var_mask, stack_depth=low.max_depth,
-        n_nodes=max(low.n_nodes, 1), flops=low.flops + 3, sfu=low.sfu, expr=expr)
+        n_nodes=max(low.n_nodes, 1), flops=low.flops + 3, sfu=low.sfu, _expr=expr)
 
 
 def compile_skeleton(expr_str, k, variables):
     """Compile the reference's c-named infix string (``bfgs.py:69-71``)."""
-    return compile_sympy(sp.sympify(expr_str), k, variables)
+    prog = compile_sympy(parse_skeleton(expr_str), k, variables)
+    prog.source = expr_str
+    return prog

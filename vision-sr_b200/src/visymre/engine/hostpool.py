@@ -34,6 +34,13 @@ def _init_worker(paths):
     os.environ["VSR_HOST_WORKERS"] = "0"          # workers never start pools of their own
     os.environ["CUDA_VISIBLE_DEVICES"] = ""       # ... and never touch the GPU
     from ..architectures import bfgs  # noqa: F401  (sympy and the compiler, imported once)
+    # a full collection over sympy's caches stalls a task for 50-100 ms -- and the whole beam waits for
+    # its slowest task: park what exists now in the permanent generation and collect the young
+    # generation rarely (sympy's trees are acyclic; its caches are bounded)
+    import gc
+    gc.collect()
+    gc.freeze()
+    gc.set_threshold(50_000, 50, 1000)
 
 
 def get_pool(n):
@@ -94,6 +101,13 @@ def compile_chunk(job):
         except Exception as exc:  # noqa: BLE001 -- per candidate, like bfgs_wrapper (model.py:15-19)
             out.append(_portable(exc))
     return out
+
+
+def prune_task(job):
+    """(Program, indices of its small constants, variables) -> architectures/bfgs.py:prepare_prune."""
+    from ..architectures import bfgs as vb
+    prog, small, variables = job
+    return vb.prepare_prune(prog, small, variables)
 
 
 def format_chunk(job):
