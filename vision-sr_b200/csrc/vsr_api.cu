@@ -33,8 +33,9 @@ struct DevBuf {
     if (p) cudaFree(p);  // synchronises: nothing in flight can still use the old block
     p = nullptr;
     cap = 0;
-    size_t want = std::max(bytes, (size_t)4096);
-    want = (want * 3) / 2;
+    // generous first size and doubling: a cudaFree synchronises the whole device, which stalls a
+    // caller that overlaps this handle's work with another handle's running fit
+    size_t want = std::max(bytes * 2, (size_t)256 * 1024);
     cudaError_t e = cudaMalloc(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;

@@ -221,38 +221,75 @@ def _host_workers(cfg):
     return hostpool.default_workers() if n is None else int(n)
 
 
+class _Compiling:
+    """Skeleton compilation of a beam under way: cache hits are there at once, the misses are tasks in
+    the host pool (heaviest skeletons first).  ``wait(indices)`` blocks until those candidates are
+    compiled; ``out[i]`` is then ``(expr, k, Program)`` or the ``Exception`` candidate i raised."""
+
+    def __init__(self, pred_strs, cfg, test_data, variables):
+        self.keys = keys = [_cache_key(t, cfg, test_data, variables) for t in pred_strs]
+        self.out = out = [_COMPILED.get(k) for k in keys]
+        miss = [i for i, h in enumerate(out) if h is None]
+        self.first = first = {}
+        for i in miss:                        # a beam may hold the same token sequence twice
+            first.setdefault(keys[i], i)
+        todo = sorted(first.values())
+        self.dup = [i for i in miss if first[keys[i]] != i]
+        self.pending = []                     # (future, candidate indices), in submission order
+        self.owner = {}                       # candidate -> position in pending
+        c_id = next((i for i, w in test_data.id2word.items() if w in ("c", "constant")), 3)
+        # weight: constants first (the iteration cap of a run is 200 k, bfgs.py:115), then length
+        self.weight = [(sum(1 for t in k[0] if t == c_id), len(k[0])) for k in keys]
+        pool = hostpool.get_pool(_host_workers(cfg)) if len(todo) >= 8 else None
+        if pool is not None:
+            # small tasks, heaviest skeletons first: the workers stay evenly loaded to the end and the
+            # candidates with the longest fits are ready first
+            todo.sort(key=lambda i: self.weight[i], reverse=True)
+            per = max(1, min(4, len(todo) // (3 * hostpool._POOL_N)))
+            bits = (bool(_opt(cfg, "add_coefficients_if_not_existing", False)),)
+            id2word = dict(test_data.id2word)
+            for j in range(0, len(todo), per):
+                ch = todo[j:j + per]
+                fut = pool.submit(hostpool.compile_chunk, ([list(keys[i][0]) for i in ch], bits, id2word, list(variables)))
+                for i in ch:
+                    self.owner[i] = len(self.pending)
+                self.pending.append((fut, ch))
+        else:
+            for i in todo:
+                try:
+                    out[i] = _remember(keys[i], compile_tokens(pred_strs[i], cfg, test_data, variables))
+                except Exception as exc:  # noqa: BLE001 -- the wrapper's contract (model.py:15-19)
+                    out[i] = exc
+            self._fill_dups()
+
+    @property
+    def staged(self):
+        return bool(self.pending)
+
+    def _fill_dups(self):
+        for i in self.dup:
+            if self.out[i] is None and self.out[self.first[self.keys[i]]] is not None:
+                self.out[i] = self.out[self.first[self.keys[i]]]
+
+    def wait(self, indices=None):
+        want = range(len(self.out)) if indices is None else indices
+        need = sorted({self.owner[j] for i in want for j in [self.first.get(self.keys[i], i)]
+                       if self.out[i] is None and j in self.owner})
+        for pos in need:
+            fut, ch = self.pending[pos]
+            if fut is None:
+                continue
+            for i, r in zip(ch, fut.result()):
+                self.out[i] = r if isinstance(r, Exception) else _remember(self.keys[i], r)
+            self.pending[pos] = (None, ch)
+        self._fill_dups()
+        return self.out
+
+
 def _compile_candidates(pred_strs, cfg, test_data, variables):
     """``(expr, k, Program)`` or the raised ``Exception`` for every candidate.  Cache misses are
-    compiled in the host pool, in chunks (sympy: 3-8 ms per candidate), when there are enough."""
-    keys = [_cache_key(t, cfg, test_data, variables) for t in pred_strs]
-    out = [_COMPILED.get(k) for k in keys]
-    miss = [i for i, h in enumerate(out) if h is None]
-    first = {}
-    for i in miss:                        # a beam may hold the same token sequence twice
-        first.setdefault(keys[i], i)
-    todo = sorted(first.values())
-    pool = hostpool.get_pool(_host_workers(cfg)) if len(todo) >= 8 else None
-    if pool is not None:
-        # small tasks, longest skeletons first: the workers stay evenly loaded to the end
-        todo.sort(key=lambda i: -len(keys[i][0]))
-        per = max(1, min(4, len(todo) // (3 * hostpool._POOL_N)))
-        chunks = [todo[j:j + per] for j in range(0, len(todo), per)]
-        bits = (bool(_opt(cfg, "add_coefficients_if_not_existing", False)),)
-        id2word = dict(test_data.id2word)
-        jobs = [([list(keys[i][0]) for i in ch], bits, id2word, list(variables)) for ch in chunks]
-        for ch, res in zip(chunks, pool.map(hostpool.compile_chunk, jobs)):
-            for i, r in zip(ch, res):
-                out[i] = r if isinstance(r, Exception) else _remember(keys[i], r)
-    else:
-        for i in todo:
-            try:
-                out[i] = _remember(keys[i], compile_tokens(pred_strs[i], cfg, test_data, variables))
-            except Exception as exc:  # noqa: BLE001 -- the wrapper's contract (model.py:15-19)
-                out[i] = exc
-    for i in miss:
-        if out[i] is None:
-            out[i] = out[first[keys[i]]]
-    return out
+    compiled in the host pool, in small tasks (sympy: 3-8 ms per candidate), when there are enough."""
+    return _Compiling(pred_strs, cfg, test_data, variables).wait()
 
 
 class LazyStr:
@@ -385,20 +422,13 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
     variables = list(test_data.total_variables)
     R = int(_opt(cfg, "n_restarts"))
 
-    # ---- Q1-Q5 + compilation, per candidate (failures stay per candidate) ----
-    cands = []
-    for hit in _compile_candidates(pred_strs, cfg, test_data, variables):
-        c = _Candidate()
-        if isinstance(hit, Exception):
-            c.error = hit
-        else:
-            c.expr, c.k, c.prog = hit
-        cands.append(c)
-    live = [i for i, c in enumerate(cands) if c.error is None]
-    results = [c.error for c in cands]
-    _mark("compile")
-    if not live:
-        return results
+    # ---- Q1-Q5 + compilation, per candidate (failures stay per candidate): started here, collected
+    # stage by stage below, while the GPU already fits the candidates that are ready ----
+    comp = _Compiling(pred_strs, cfg, test_data, variables)
+    n_cand = len(pred_strs)
+    cands = [None] * n_cand
+    if not comp.staged and all(isinstance(h, Exception) for h in comp.out):
+        return list(comp.out)     # nothing to fit: the engine is not touched
 
     # ---- Q6 outlier rows ----
     rows_removed = False
@@ -426,43 +456,103 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
     score_dtype = fitter.F32 if Xt.dtype == torch.float32 else fitter.F64
     eval_dtype = fitter.F32 if str(_opt(cfg, "precision", "fp64")).lower() == "fp32" else fitter.F64
     eng.set_points(Xt[0], yt_fit, dtypes=tuple({eval_dtype, score_dtype, fitter.F64}))
-    eng.set_programs([cands[i].prog for i in live])
     opts = _engine_opts(cfg, scale, eval_dtype, score_dtype)
+    main_stream = torch.cuda.current_stream(eng.device)
+    points_ready = torch.cuda.Event()
+    points_ready.record(main_stream)      # side streams wait for the upload, not for the first stage's fit
     _mark("upload")
 
-    # ---- Q8 restarts: one run per (candidate, restart) ----
-    kmax = max(1, max(cands[i].k for i in live))
-    start = np.zeros((len(live) * R, kmax), dtype=np.float64)
-    run_prog, run_slot = [], []
-    for li, ci in enumerate(live):
-        k = cands[ci].k
-        for r in range(R):
-            if x0 is not None and x0[ci] is not None:
-                v = np.asarray(x0[ci], dtype=np.float64)[r][:k]
-            else:
-                v = np.random.randn(k) * 10
-            start[li * R + r, :k] = v
-            run_prog.append(li)
-            run_slot.append(li * R + r)
     world = sharding.world_size() if _opt(cfg, "shard", True) and not rows_removed else 1
-    if world > 1:
-        # the (candidate, restart) runs of the beam are dealt over the ranks of the default
-        # process group, every rank fits its share, ONE all-gather brings back a record per candidate
-        # (score, restart, constants) and every rank takes the same argmin.  Every rank must have
-        # been called with the same candidates and points; the starting points are rank 0's.
-        start_dev = sharding.broadcast_from_rank0(torch.from_numpy(start).to(eng.device))
-        cost = np.repeat([(cands[ci].k + 1.0) * cands[ci].prog.n_insns for ci in live], R)
-        win, _ = sharding.fit_sharded(eng, [cands[ci].k for ci in live], R, start_dev, opts, cost=cost,
-                                      key_dtype=torch.float32 if score_dtype == fitter.F32 else None)
-        win = win.cpu().numpy()
+    # Stages: the candidates with the most constants (longest fits; their skeletons are compiled
+    # first) are fitted as soon as THEY are compiled, on the main engine; the rest follows on a side
+    # engine and stream that shares the points.  One stage when there is nothing to overlap.
+    if comp.staged and world == 1 and n_cand >= 24 and _opt(cfg, "pipeline", True):
+        order = sorted(range(n_cand), key=lambda i: comp.weight[i], reverse=True)
+        # a first stage that fills the GPU (8 candidates x R restarts) is ready after one round of
+        # compile tasks; the second takes the next quarter, the third the rest
+        cuts = [0, 8, 8 + max(8, n_cand // 4), n_cand]
+        stages = [sorted(order[a:b]) for a, b in zip(cuts, cuts[1:]) if b > a]
     else:
-        res = eng.fit(run_prog, run_slot, torch.from_numpy(start), opts)
+        stages = [list(range(n_cand))]
+
+    def _collect(stage):
+        comp.wait(stage)
+        for i in stage:
+            hit = comp.out[i]
+            c = _Candidate()
+            if isinstance(hit, Exception):
+                c.error = hit
+            else:
+                c.expr, c.k, c.prog = hit
+            cands[i] = c
+        return [i for i in stage if cands[i].error is None]
+
+    def _starts(live_s):
+        # ---- Q8 restarts: one run per (candidate, restart) ----
+        kmax = max(1, max(cands[i].k for i in live_s))
+        start = np.zeros((len(live_s) * R, kmax), dtype=np.float64)
+        for li, ci in enumerate(live_s):
+            k = cands[ci].k
+            for r in range(R):
+                if x0 is not None and x0[ci] is not None:
+                    v = np.asarray(x0[ci], dtype=np.float64)[r][:k]
+                else:
+                    v = np.random.randn(k) * 10
+                start[li * R + r, :k] = v
+        return start
+
+    fitted = {}     # candidate -> (lastx rows [R, k], final scores [R])   (one GPU)
+    win_of = {}     # candidate -> record of the all-gather                (sharded)
+    launched = []
+    for si, stage in enumerate(stages):
+        live_s = _collect(stage)
+        _mark("compile")
+        if not live_s:
+            continue
+        start = _starts(live_s)
+        if world > 1:
+            # the (candidate, restart) runs of the beam are dealt over the ranks of the default
+            # process group, every rank fits its share, ONE all-gather brings back a record per candidate
+            # (score, restart, constants) and every rank takes the same argmin.  Every rank must have
+            # been called with the same candidates and points; the starting points are rank 0's.
+            eng.set_programs([cands[i].prog for i in live_s])
+            start_dev = sharding.broadcast_from_rank0(torch.from_numpy(start).to(eng.device))
+            cost = np.repeat([(cands[ci].k + 1.0) * cands[ci].prog.n_insns for ci in live_s], R)
+            win, _ = sharding.fit_sharded(eng, [cands[ci].k for ci in live_s], R, start_dev, opts, cost=cost,
+                                          key_dtype=torch.float32 if score_dtype == fitter.F32 else None)
+            win = win.cpu().numpy()
+            for li, ci in enumerate(live_s):
+                win_of[ci] = win[li]
+            continue
+        run_prog = np.repeat(np.arange(len(live_s), dtype=np.int32), R)
+        run_slot = np.arange(len(live_s) * R, dtype=np.int32)
+        if si == 0:
+            eng.set_programs([cands[i].prog for i in live_s])
+            res = eng.fit(run_prog, run_slot, torch.from_numpy(start), opts)
+        else:
+            side = fitter.get_side_engine(eng, si)
+            side.adopt_points(eng)
+            stream = fitter.side_stream(eng.device, si)
+            stream.wait_event(points_ready)       # the points are uploaded on the caller's stream
+            with torch.cuda.stream(stream):
+                side.set_programs([cands[i].prog for i in live_s])
+                res = side.fit(run_prog, run_slot, torch.from_numpy(start), opts)
+            main_stream.wait_stream(stream)
+        launched.append((live_s, res))
+        _mark("launch")
+    for live_s, res in launched:
         lastx = res.lastx.cpu().numpy()
         final = res.final_mse.cpu().numpy()
         if score_dtype == fitter.F32:
             final = final.astype(np.float32)
         if rows_removed:
             final = np.full_like(final, 1e9)  # y_found - y raises on the shape mismatch (bfgs.py:130-131)
+        for li, ci in enumerate(live_s):
+            fitted[ci] = (lastx[li * R:(li + 1) * R], final[li * R:(li + 1) * R])
+    live = [i for i, c in enumerate(cands) if c.error is None]
+    results = [c.error for c in cands]
+    if not live:
+        return results
 
     _mark("fit")
     # ---- Q10/Q11 pick the restart, Q12 collect prune work ----
@@ -470,18 +560,18 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
     tol = _opt(cfg, "prune_tolerance", 1.05)
     picked = {}
     prune_jobs, prune_todo = [], []
-    for li, ci in enumerate(live):
+    for ci in live:
         c = cands[ci]
         if world > 1:
-            best_consts = win[li, 3:3 + c.k].copy()
-            best_loss = np.float32(win[li, -1]) if score_dtype == fitter.F32 else win[li, -1]
+            best_consts = win_of[ci][3:3 + c.k].copy()
+            best_loss = np.float32(win_of[ci][-1]) if score_dtype == fitter.F32 else win_of[ci][-1]
         else:
-            F_loss = final[li * R:(li + 1) * R]
+            lastx, F_loss = fitted[ci]
             try:
                 k_best = int(np.nanargmin(F_loss))
             except ValueError:
                 k_best = 0
-            best_consts = lastx[li * R + k_best, :c.k].copy()
+            best_consts = lastx[k_best, :c.k].copy()
             best_loss = F_loss[k_best]
         csyms = [sp.Symbol(f"c{i}") for i in range(c.k)]
         picked[ci] = [best_consts, best_loss, csyms]

@@ -149,6 +149,18 @@ class Engine:
             self._points[dt] = (Xc, yc)
         self.n_vars = n_vars
 
+    def adopt_points(self, other):
+        """Use the points another engine of the same device holds (no copy: the same device tensors
+        are registered with this handle): engines that fit parts of one beam concurrently."""
+        self._src = other._src
+        self.n_points = other.n_points
+        self.n_vars = other.n_vars
+        self._want_dtypes = tuple(other._want_dtypes)
+        self._points = dict(other._points)
+        for dt, (Xc, yc) in self._points.items():
+            self._check(self.lib.vsr_set_points(self._h, _ptr(Xc), _ptr(yc), self.n_points, int(Xc.shape[1]),
+                                                self.n_vars, dt))
+
     def ensure_dtype(self, dt):
         if dt not in self._points:
             self._want_dtypes = tuple(self._want_dtypes) + (dt,)
@@ -287,3 +299,23 @@ def get_engine(device=None):
     if index not in _ENGINES:
         _ENGINES[index] = Engine(torch.device("cuda", index))
     return _ENGINES[index]
+
+
+_SIDE = {}
+_SIDE_STREAMS = {}
+
+
+def get_side_engine(main, i):
+    """i-th helper engine beside ``main`` (same device): fits another part of the same beam."""
+    key = (id(main), i)
+    if key not in _SIDE:
+        _SIDE[key] = Engine(main.device)
+    return _SIDE[key]
+
+
+def side_stream(device, i):
+    dev = torch.device(device)
+    key = (dev.index, i)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
