@@ -468,10 +468,9 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
     # engine and stream that shares the points.  One stage when there is nothing to overlap.
     if comp.staged and world == 1 and n_cand >= 24 and _opt(cfg, "pipeline", True):
         order = sorted(range(n_cand), key=lambda i: comp.weight[i], reverse=True)
-        # a first stage that fills the GPU (8 candidates x R restarts) is ready after one round of
-        # compile tasks; the second takes the next quarter, the third the rest
-        cuts = [0, 8, 8 + max(8, n_cand // 4), n_cand]
-        stages = [sorted(order[a:b]) for a, b in zip(cuts, cuts[1:]) if b > a]
+        # (three stages -- 8 candidates, a quarter, the rest -- measured no better than two)
+        n_first = max(8, (n_cand + 2) // 3)
+        stages = [sorted(order[:n_first]), sorted(order[n_first:])]
     else:
         stages = [list(range(n_cand))]
 
