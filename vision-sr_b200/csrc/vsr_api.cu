@@ -798,14 +798,24 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
   }
   // widest groups first: their runs have the highest iteration caps (200 k)
   std::stable_sort(groups.begin(), groups.end(), [](const Group& x, const Group& y) { return x.kmax > y.kmax; });
-  // potentially longest runs first (iteration cap is 200 k, cost per pass grows with the
-  // program) so the tail of the launch is short runs
+  // Queue order of a group.  Runs with more constants first (iteration cap 200 k); among those,
+  // the runs of ONE program (the restarts of a candidate) are spread out: r-th restart of every
+  // program before the (r+1)-th of any.  A hard candidate tends to drive most of its restarts to the
+  // iteration cap, and the seats of a cluster take consecutive queue entries when the launch starts:
+  // candidate-major order put four capped runs into one cluster (each then advances at a quarter of
+  // the cluster's sweep rate) while other clusters ran dry.
+  const bool by_candidate = getenv("VSR_QUEUE_BY_CANDIDATE") != nullptr;  // measurement hook: the old order
   for (auto& g : groups) {
-    std::vector<int> order(g.prog.size());
+    std::vector<int> order(g.prog.size()), rep(g.prog.size());
+    {
+      std::vector<int> seen(h->n_programs, 0);
+      for (size_t i = 0; i < order.size(); ++i) rep[i] = seen[g.prog[i]]++;
+    }
     for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
       const int ka = h->h_k[g.prog[a]], kb = h->h_k[g.prog[b]];
       if (ka != kb) return ka > kb;
+      if (!by_candidate && rep[a] != rep[b]) return rep[a] < rep[b];
       return h->h_ninsn[g.prog[a]] > h->h_ninsn[g.prog[b]];
     });
     std::vector<int32_t> p2(order.size()), s2(order.size());

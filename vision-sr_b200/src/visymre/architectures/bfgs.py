@@ -129,10 +129,11 @@ def prepare_prune(prog, small, variables):
         return None
     rest = [i for i in range(prog.k) if i not in zero_idx]
     if rest:
+        # like the reference (bfgs.py:161-168): zeros substituted, the remaining symbols keep their
+        # names and become arguments in their order (no renaming, so no re-canonicalisation)
         pruned = prog.expr.subs({csyms[i]: 0.0 for i in zero_idx})
-        pruned = pruned.xreplace({csyms[i]: sp.Symbol(f"c{j}") for j, i in enumerate(rest)})
         try:
-            out = compile_sympy(pruned, len(rest), variables)
+            out = compile_sympy(pruned, len(rest), variables, slots={i: j for j, i in enumerate(rest)})
         except CompileError:
             return None
         out._expr = None           # nobody reads the pruned tree again
@@ -145,12 +146,14 @@ def prepare_prune(prog, small, variables):
     return zero_idx, rest, None, zprog
 
 
-def _prepare_prunes(items, variables, cfg):
-    pool = hostpool.get_pool(_host_workers(cfg)) if len(items) >= 4 else None
+def _prepare_prune_async(prog, small, variables, cfg, many=True):
+    """``prepare_prune`` of one candidate: in the host pool when there is one and the caller has
+    several candidates to prepare.  Returns a function that waits for the result."""
+    pool = hostpool.get_pool(_host_workers(cfg)) if many else None
     if pool is None:
-        return [prepare_prune(prog, small, variables) for prog, small in items]
-    jobs = [(prog, small, list(variables)) for prog, small in items]
-    return list(pool.map(hostpool.prune_task, jobs))
+        got = prepare_prune(prog, small, variables)
+        return lambda: got
+    return pool.submit(hostpool.prune_task, (prog, small, list(variables))).result
 
 
 def _derivative_is_constant(expr, sym):
@@ -536,54 +539,77 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
             with torch.cuda.stream(stream):
                 side.set_programs([cands[i].prog for i in live_s])
                 res = side.fit(run_prog, run_slot, torch.from_numpy(start), opts)
-            main_stream.wait_stream(stream)
-        launched.append((live_s, res))
+            done = torch.cuda.Event()
+            done.record(stream)
+        if si == 0:
+            stream = main_stream
+            done = torch.cuda.Event()
+            done.record(main_stream)
+        launched.append((live_s, res, stream, done))
         _mark("launch")
-    for live_s, res in launched:
-        lastx = res.lastx.cpu().numpy()
-        final = res.final_mse.cpu().numpy()
+
+    # ---- Q10/Q11 pick the restart, Q12 collect prune work: stage by stage as the fits finish, so
+    # that the symbolic half of Q12 of an early stage runs in the host pool while a later one is
+    # still on the GPU ----
+    thr = _opt(cfg, "prune_threshold", 1e-3)
+    tol = _opt(cfg, "prune_tolerance", 1.05)
+    picked = {}
+    prune_jobs, prune_waits = [], []
+
+    def _pick(ci, best_consts, best_loss):
+        c = cands[ci]
+        csyms = [sp.Symbol(f"c{i}") for i in range(c.k)]
+        picked[ci] = [best_consts, best_loss, csyms]
+        return [i for i, v in enumerate(best_consts) if abs(v) < thr] if c.k > 0 else []
+
+    for ci, rec in win_of.items():
+        k = cands[ci].k
+        small = _pick(ci, rec[3:3 + k].copy(), np.float32(rec[-1]) if score_dtype == fitter.F32 else rec[-1])
+        if small:
+            prune_waits.append((ci, _prepare_prune_async(cands[ci].prog, small, variables, cfg, many=len(win_of) >= 4)))
+    waiting = list(launched)
+    while waiting:
+        pos = next((j for j, w in enumerate(waiting) if w[3].query()), None)
+        if pos is None:
+            if len(waiting) == 1:
+                waiting[0][3].synchronize()
+            else:
+                _time.sleep(0.0002)
+            continue
+        live_s, res, stream, _ = waiting.pop(pos)
+        with torch.cuda.stream(stream):
+            lastx = res.lastx.cpu().numpy()
+            final = res.final_mse.cpu().numpy()
         if score_dtype == fitter.F32:
             final = final.astype(np.float32)
         if rows_removed:
             final = np.full_like(final, 1e9)  # y_found - y raises on the shape mismatch (bfgs.py:130-131)
+        todo = []
         for li, ci in enumerate(live_s):
-            fitted[ci] = (lastx[li * R:(li + 1) * R], final[li * R:(li + 1) * R])
-    live = [i for i, c in enumerate(cands) if c.error is None]
-    results = [c.error for c in cands]
-    if not live:
-        return results
-
-    _mark("fit")
-    # ---- Q10/Q11 pick the restart, Q12 collect prune work ----
-    thr = _opt(cfg, "prune_threshold", 1e-3)
-    tol = _opt(cfg, "prune_tolerance", 1.05)
-    picked = {}
-    prune_jobs, prune_todo = [], []
-    for ci in live:
-        c = cands[ci]
-        if world > 1:
-            best_consts = win_of[ci][3:3 + c.k].copy()
-            best_loss = np.float32(win_of[ci][-1]) if score_dtype == fitter.F32 else win_of[ci][-1]
-        else:
-            lastx, F_loss = fitted[ci]
+            F_loss = final[li * R:(li + 1) * R]
             try:
                 k_best = int(np.nanargmin(F_loss))
             except ValueError:
                 k_best = 0
-            best_consts = lastx[k_best, :c.k].copy()
-            best_loss = F_loss[k_best]
-        csyms = [sp.Symbol(f"c{i}") for i in range(c.k)]
-        picked[ci] = [best_consts, best_loss, csyms]
-        small = [i for i, v in enumerate(best_consts) if abs(v) < thr] if c.k > 0 else []
-        if small:
-            prune_todo.append((ci, small))
-    # the symbolic half of Q12 (derivative test, substitution of the zeros, lowering of the pruned
-    # skeleton) is independent per candidate: in the host pool when there are enough of them
-    prepared = _prepare_prunes([(cands[ci].prog, small) for ci, small in prune_todo], variables, cfg)
-    for (ci, small), got in zip(prune_todo, prepared):
+            small = _pick(ci, lastx[li * R + k_best, :cands[ci].k].copy(), F_loss[k_best])
+            if small:
+                todo.append((ci, small))
+        for ci, small in todo:
+            prune_waits.append((ci, _prepare_prune_async(cands[ci].prog, small, variables, cfg, many=len(todo) >= 4)))
+    for _, _, stream, _ in launched:
+        if stream is not main_stream:
+            main_stream.wait_stream(stream)
+    live = [i for i, c in enumerate(cands) if c is not None and c.error is None]
+    results = [None if c is None else c.error for c in cands]
+    if not live:
+        return results
+    _mark("fit")
+    for ci, wait in prune_waits:
+        got = wait()
         if got is not None:
             zero_idx, rest, prog, zprog = got
             prune_jobs.append(dict(ci=ci, zero=zero_idx, rest=rest, prog=prog, zprog=zprog))
+    prune_jobs.sort(key=lambda j: j["ci"])
 
     _mark("prune_sym")
     # ---- Q12 re-fit the pruned skeletons (one more BFGS each, from the best point) ----

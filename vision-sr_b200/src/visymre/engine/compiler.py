@@ -119,8 +119,9 @@ def _powi_cost(n):
 
 
 class _Lowering:
-    def __init__(self, k, variables):
+    def __init__(self, k, variables, slots=None):
         self.k = k
+        self.slots = slots      # {i: slot} when the constants c_i keep their names (pruned skeletons)
         self.var_index = {v: i for i, v in enumerate(variables)}
         self.code = []
         self.imms = []
@@ -146,6 +147,15 @@ class _Lowering:
             self.imms.append(value)
         return self.imm_index[key]
 
+    def const_slot(self, name):
+        """Slot of the fitted constant called `name` (``c<i>``), None if it is not one."""
+        if name[0] != "c" or not name[1:].isdigit():
+            return None
+        j = int(name[1:])
+        if self.slots is not None:
+            return self.slots.get(j)
+        return j if j < self.k else None
+
     def leaf(self, node):
         """(src, idx, tangent mask) if `node` is a leaf operand, else None (memoised: the
         emitter asks several times per node and free_symbols walks the whole subtree)."""
@@ -160,8 +170,8 @@ class _Lowering:
             name = node.name
             if name in self.var_index:
                 return SRC["VSR_SRC_VAR"], self.var_index[name], 0
-            if name[0] == "c" and name[1:].isdigit() and int(name[1:]) < self.k:
-                j = int(name[1:])
+            j = self.const_slot(name)
+            if j is not None:
                 return SRC["VSR_SRC_CONST"], j, (1 << j) if j < isa.MAX_DUAL else 0
             raise CompileError(f"unknown symbol {name!r}")
         if isinstance(node, sp.Number) or node in (sp.pi, sp.E) or isinstance(node, sp.NumberSymbol):
@@ -192,11 +202,9 @@ class _Lowering:
         if m is None:
             m = 0
             for s in node.free_symbols:
-                n = s.name
-                if n[0] == "c" and n[1:].isdigit():
-                    j = int(n[1:])
-                    if j < self.k and j < isa.MAX_DUAL:
-                        m |= 1 << j
+                j = self.const_slot(s.name)
+                if j is not None and j < isa.MAX_DUAL:
+                    m |= 1 << j
             self._tmask[node] = m
         return m
 
@@ -405,14 +413,16 @@ def _peephole(code):
     return out
 
 
-def compile_sympy(expr, k, variables):
-    """Lower a sympy expression in the symbols ``variables`` and ``c0..c{k-1}``."""
+def compile_sympy(expr, k, variables, slots=None):
+    """Lower a sympy expression in the symbols ``variables`` and ``c0..c{k-1}``.  ``slots``: the
+    fitted constants are the symbols ``c<i>`` for i in ``slots``, at slot ``slots[i]`` (the reference
+    lambdifies a pruned loss over the REMAINING symbols under their own names, bfgs.py:161-168)."""
     if k > isa.MAX_CONSTS:
         raise CompileError(f"{k} constants exceed the limit of {isa.MAX_CONSTS}")
     expr = sp.sympify(expr)
     if expr.has(sp.I) or expr.has(sp.zoo) or expr.has(sp.nan) or expr.has(sp.oo):
         raise CompileError(f"non-real expression {expr}")
-    low = _Lowering(k, list(variables))
+    low = _Lowering(k, list(variables), slots)
     low.gen(expr)
     low.emit("VSR_END")
     low.code = _peephole(low.code)
