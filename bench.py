@@ -349,7 +349,7 @@ def run_reference(args):
                              "sample": f"all {args.cand} candidates of {steps} beams, one pool of {arm.cores} worker processes, "
                                        f"{dt:.1f} s, nfev {nfev}", "seconds": dt, "nfev": nfev},
             "e2e": {"value": v, "unit": "candidate-fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args):
@@ -362,8 +362,21 @@ def workload_config(args):
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
+def emit(line):
+    """The ONE line of stdout: everything else a library prints there (NCCL's version banner ...) was
+    sent to stderr by main()."""
+    os.write(_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_STDOUT = 1
+
+
 def main():
+    global _STDOUT
     args = parse()
+    sys.stdout.flush()
+    _STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -716,7 +729,7 @@ def main():
             line["replicas"] = replicas
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline([beams[bi] for bi in timed], args, args.cpu_seconds)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -45,6 +45,10 @@ def test_merge_equals_nanargmin_single_process():
     fm[rng.rand(C * R) < 0.3] = np.nan
     fm[5 * R:6 * R] = np.nan                 # an all-nan candidate
     fm[7 * R + 2] = fm[7 * R + 6] = 0.0      # a tie
+    fm[9 * R:10 * R] = np.nan                # nans and real +inf scores only: np.nanargmin takes the first inf
+    fm[9 * R + 4] = fm[9 * R + 7] = np.inf
+    fm[11 * R:12 * R] = np.inf               # all +inf
+    fm[11 * R] = np.nan
     loss = rng.rand(C * R)
     consts = rng.rand(C * R, kmax)
     parts = sharding.partition_runs(rng.rand(C * R), world)
@@ -55,7 +59,7 @@ def test_merge_equals_nanargmin_single_process():
         f = torch.full((C * R,), float("nan"), dtype=torch.float64)
         f[mine] = torch.as_tensor(fm)[mine]
         recs.append(sharding.local_best_records(f, torch.as_tensor(loss), torch.as_tensor(consts), C, R, mine))
-    win = sharding.merge_records(torch.stack(recs))
+    win = sharding.merge_records(torch.stack(recs), R)
     want = _single_gpu_answer(fm, R)
     assert np.array_equal(win[:, 1].numpy().astype(int), want)
     rows = np.arange(C) * R + want
@@ -74,12 +78,13 @@ WORKER = textwrap.dedent("""
     rng = np.random.RandomState(3)
     C, R, kmax = 23, 8, 3
     fm = rng.rand(C * R); fm[rng.rand(C * R) < 0.25] = np.nan; fm[2*R:3*R] = np.nan
+    fm[4*R:5*R] = np.nan; fm[4*R+3] = fm[4*R+6] = np.inf
     loss = rng.rand(C * R); consts = rng.rand(C * R, kmax)
     parts = sharding.partition_runs(rng.rand(C * R), world)
     mine = torch.zeros(C * R, dtype=torch.bool); mine[torch.as_tensor(parts[rank])] = True
     f = torch.full((C * R,), float("nan"), dtype=torch.float64); f[mine] = torch.as_tensor(fm)[mine]
     rec = sharding.local_best_records(f, torch.as_tensor(loss), torch.as_tensor(consts), C, R, mine)
-    win = sharding.allgather_best(rec)
+    win = sharding.allgather_best(rec, n_restarts=R)
     want = []
     for c in range(C):
         row = fm[c*R:(c+1)*R]

@@ -41,9 +41,8 @@ def local_best_records(final_mse, loss, consts, n_cand, n_restarts, mine, key_dt
     """Per-candidate best of THIS rank's restarts.
 
     final_mse, loss: [C*R]; consts: [C*R, kmax]; mine: bool [C*R], runs this rank fitted.
-    Returns a float64 tensor [C, 3 + kmax]: (final_mse or +inf, restart index, loss, consts).
-    A rank that holds no finite score for a candidate reports +inf with its lowest own
-    restart (or R when it holds none), so an all-nan candidate falls back to restart 0.
+    Returns a float64 tensor [C, 4 + kmax]: (score with nan counted as +inf, restart index (R when
+    the rank holds no run of the candidate), loss, consts, raw score).
     """
     dev = final_mse.device
     C, R = n_cand, n_restarts
@@ -53,15 +52,18 @@ def local_best_records(final_mse, loss, consts, n_cand, n_restarts, mine, key_dt
         fm = fm.to(key_dtype).to(torch.float64)
     own = mine.reshape(C, R)
     ridx = torch.arange(R, device=dev).expand(C, R)
-    key = torch.where(own & ~torch.isnan(fm), fm, torch.full_like(fm, float("inf")))
-    best_val, best_r = key.min(dim=1)          # first minimum = lowest restart on ties
-    none_finite = torch.isinf(best_val) & ~((key == float("inf")) & own & ~torch.isnan(fm)).any(dim=1)
-    lowest_own = torch.where(own, ridx, torch.full_like(ridx, R)).min(dim=1).values
-    best_r = torch.where(none_finite, lowest_own.clamp(max=R - 1), best_r)
+    # np.nanargmin (bfgs.py:134-137) = first minimum with every nan counted as +inf (an all-nan list
+    # falls back to restart 0, which is the same thing).  Here: the same rule over THIS rank's slots.
+    inf = torch.full_like(fm, float("inf"))
+    key = torch.where(torch.isnan(fm), inf, fm)
+    best_val = torch.where(own, key, inf).min(dim=1).values
+    hit = own & (key == best_val[:, None])
+    best_own = torch.where(hit, ridx, torch.full_like(ridx, R)).min(dim=1).values   # R: holds no run of it
+    best_r = best_own.clamp(max=R - 1)
     rec = torch.zeros((C, 3 + kmax), dtype=torch.float64, device=dev)
     rows = torch.arange(C, device=dev) * R + best_r
     rec[:, 0] = best_val
-    rec[:, 1] = torch.where(none_finite, lowest_own, best_r).to(torch.float64)
+    rec[:, 1] = best_own.to(torch.float64)
     rec[:, 2] = loss.reshape(-1)[rows]
     rec[:, 3:] = consts[rows]
     # keep the raw score (nan stays nan) for the winner's report
@@ -70,7 +72,7 @@ def local_best_records(final_mse, loss, consts, n_cand, n_restarts, mine, key_dt
     return rec
 
 
-def merge_records(all_recs):
+def merge_records(all_recs, n_restarts=None):
     """all_recs: [world, C, 4 + kmax] gathered records -> [C, 4 + kmax] winners.
 
     Order of preference: smaller finite score, then lower restart index.
@@ -86,14 +88,14 @@ def merge_records(all_recs):
     return all_recs[winner, torch.arange(C, device=all_recs.device)]
 
 
-def allgather_best(rec, group=None):
+def allgather_best(rec, group=None, n_restarts=None):
     """One all-gather of the per-candidate records; every rank returns the same winners."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return merge_records(rec[None])
+        return merge_records(rec[None], n_restarts)
     world = dist.get_world_size(group)
     parts = [torch.empty_like(rec) for _ in range(world)]
     dist.all_gather(parts, rec.contiguous(), group=group)   # the path's only collective
-    return merge_records(torch.stack(parts))
+    return merge_records(torch.stack(parts), n_restarts)
 
 
 def empty_result(n_slots, kstride, device):
@@ -132,4 +134,4 @@ def fit_sharded(engine, programs_k, n_restarts, x0, opts, cost=None, group=None,
     mine = torch.zeros(C * R, dtype=torch.bool, device=res.loss.device)
     mine[torch.as_tensor(mine_idx, device=mine.device)] = True
     rec = local_best_records(res.final_mse, res.loss, res.lastx, C, R, mine, key_dtype)
-    return allgather_best(rec, group), res
+    return allgather_best(rec, group, n_restarts=R), res
