@@ -301,22 +301,29 @@ def _noop(i):
 
 
 def cpu_baseline(beams, args, budget_s):
-    """candidate-fits/s of the CPU arm on whole beams of the timed workload, until the budget is spent."""
+    """candidate-fits/s of the CPU arm on the timed workload: whole beams while they fit the budget,
+    else the first candidates of the first beam (the sample is sized from an untimed probe of one
+    candidate per core)."""
     kind = cpu_kind(args)
     arm = CpuArm(kind, args.restarts)
-    arm.step(beams[0], limit=arm.cores)        # imports / first-call costs, untimed
+    C = len(beams[0].tokens)
+    _, t_probe, _ = arm.step(beams[0], limit=arm.cores)        # imports / first-call costs, untimed
+    rounds = max(1, int(budget_s / max(t_probe, 1e-3)))
+    limit = None if rounds * arm.cores >= C else rounds * arm.cores
     n = dt = nfev = 0
     t_all = time.time()
     used = 0
     for b in beams:
-        a, d, f = arm.step(b)
+        a, d, f = arm.step(b, limit=limit)
         n, dt, nfev, used = n + a, dt + d, nfev + f, used + 1
-        if time.time() - t_all > budget_s:
+        if limit is not None or time.time() - t_all + d > budget_s:
             break
     arm.close()
     N = beams[0].X.shape[0]
+    what = (f"all {C} candidates of the first {used} timed beams" if limit is None
+            else f"the first {limit} of the {C} candidates of the first timed beam")
     return {"value": n / dt, "unit": "candidate-fits/s", "cores": arm.cores, "kind": kind,
-            "sample": f"all {len(beams[0].tokens)} candidates of the first {used} timed beams (R={args.restarts}, N={N}), "
+            "sample": f"{what} (R={args.restarts}, N={N}), "
                       + ("the unmodified reference's bfgs_wrapper (oracle/_ref)" if kind == "reference"
                          else "oracle/vectorised.py (scipy BFGS over numpy columns)")
                       + f" in {arm.cores} worker processes, {dt:.1f} s, nfev {nfev}",
@@ -331,9 +338,13 @@ def run_reference(args):
     kind = cpu_kind(args)
     arm = CpuArm(kind, args.restarts)
     n = dt = nfev = steps = 0
+    # a step = all candidates of a beam while that takes under ~12 s, else a bounded sample of them
+    _, t_probe, _ = arm.step(beams[0], limit=arm.cores)
+    rounds = max(1, int(12.0 / max(t_probe, 1e-3)))
+    limit = None if rounds * arm.cores >= args.cand else rounds * arm.cores
     t_all = time.time()
     for s in range(args.warmup + args.steps):
-        a, d, f = arm.step(beams[s])
+        a, d, f = arm.step(beams[s], limit=limit)
         if s >= args.warmup:
             n, dt, nfev, steps = n + a, dt + d, nfev + f, steps + 1
         if time.time() - t_all > 240 and steps >= 2:
@@ -346,7 +357,7 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args),
             "cpu_baseline": {"value": v, "unit": "candidate-fits/s", "cores": arm.cores, "kind": kind,
-                             "sample": f"all {args.cand} candidates of {steps} beams, one pool of {arm.cores} worker processes, "
+                             "sample": f"{'all ' + str(args.cand) if limit is None else 'the first ' + str(limit) + ' of the ' + str(args.cand)} candidates of {steps} beams, one pool of {arm.cores} worker processes, "
                                        f"{dt:.1f} s, nfev {nfev}", "seconds": dt, "nfev": nfev},
             "e2e": {"value": v, "unit": "candidate-fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)

@@ -1,9 +1,8 @@
 """Recipe for oracle/_ref: the UNMODIFIED reference hot path, byte-compiled where it lies.
 
 The reference is pure Python (no build system).  This script compiles the few modules its
-``bfgs()`` needs -- straight from ``/root/reference/src/visymre`` -- to SOURCELESS ``.pyc`` files
-under ``oracle/_ref/src/visymre/...`` (``py_compile``; no reference source text is copied into the
-repo) and extracts the pickled vocabulary record from ``scripts/weights/meta/metadata.h5`` (bytes
+``bfgs()`` needs -- straight from ``/root/reference/src/visymre`` -- to code objects in ONE
+archive ``oracle/_ref/modules.bin`` (no reference source text is copied into the repo) and extracts the pickled vocabulary record from ``scripts/weights/meta/metadata.h5`` (bytes
 2048..4974).  ``oracle/_ref/`` is git-ignored but travels to the GPU box, where
 ``/root/reference`` does not exist: there ``bench.py --impl reference --config 1`` times this
 as-is reference (``cpu_baseline.kind = "reference"``) and ``oracle/ref_harness.load()`` finds it.
@@ -12,7 +11,6 @@ Run:  python oracle/build_ref.py      (``__graft_entry__.build()`` does, when /r
 TEST INFRASTRUCTURE: nothing under vision-sr_b200/ imports oracle/.
 """
 import os
-import py_compile
 import shutil
 import sys
 
@@ -31,31 +29,39 @@ MODULES = [
 
 
 def build(ref=REF, out=OUT):
+    """One archive, ``oracle/_ref/modules.bin``: {dotted module name: (is_package, marshalled code
+    object)} of the reference's own modules, compiled from where they lie (``compile()`` +
+    ``marshal``: what a ``.pyc`` holds, without the file names a snapshot tool may filter)."""
+    import marshal
+    import pickle
     if not os.path.isdir(ref):
         raise FileNotFoundError(f"{ref} is not here: oracle/_ref can only be built in the build container")
     if os.path.isdir(out):
         shutil.rmtree(out)
-    n = 0
+    os.makedirs(out)
+    mods = {}
     for rel in MODULES:
         src = os.path.join(ref, rel)
-        dst = os.path.join(out, rel + "c")          # module.pyc beside where module.py would be
-        os.makedirs(os.path.dirname(dst), exist_ok=True)
-        if not os.path.exists(src):
-            if rel.endswith("__init__.py"):         # namespace package in the reference: an empty module
-                tmp = dst[:-1] + ".empty"
-                open(tmp, "w").close()
-                py_compile.compile(tmp, cfile=dst, doraise=True, dfile=rel)
-                os.remove(tmp)
-                n += 1
+        is_pkg = rel.endswith("__init__.py")
+        name = rel[:-3].replace("/", ".")
+        if is_pkg:
+            name = name[: -len(".__init__")]
+        if os.path.exists(src):
+            with open(src, "rb") as fh:
+                code = compile(fh.read(), src, "exec", dont_inherit=True)
+        elif is_pkg:                                # namespace package in the reference: an empty module
+            code = compile("", rel, "exec")
+        else:
             continue
-        py_compile.compile(src, cfile=dst, doraise=True, dfile=src)
-        n += 1
+        mods[name] = (is_pkg, marshal.dumps(code))
+    with open(os.path.join(out, "modules.bin"), "wb") as fh:
+        pickle.dump(mods, fh)
     raw = open(os.path.join(ref, "scripts/weights/meta/metadata.h5"), "rb").read()
     with open(os.path.join(out, "metadata.pkl"), "wb") as fh:
         fh.write(raw[2048:2048 + 2926])
     with open(os.path.join(out, "PYTHON"), "w") as fh:
-        fh.write(f"{sys.version_info.major}.{sys.version_info.minor}\n")   # .pyc files are per minor version
-    return n
+        fh.write(f"{sys.version_info.major}.{sys.version_info.minor}\n")   # code objects are per minor version
+    return len(mods)
 
 
 if __name__ == "__main__":
