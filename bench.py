@@ -307,7 +307,8 @@ def cpu_baseline(beams, args, budget_s):
     kind = cpu_kind(args)
     arm = CpuArm(kind, args.restarts)
     C = len(beams[0].tokens)
-    _, t_probe, _ = arm.step(beams[0], limit=arm.cores)        # imports / first-call costs, untimed
+    arm.step(beams[0], limit=arm.cores)                        # imports / first-call costs, untimed
+    _, t_probe, _ = arm.step(beams[0], limit=arm.cores)        # one candidate per core: sizes the sample
     rounds = max(1, int(budget_s / max(t_probe, 1e-3)))
     limit = None if rounds * arm.cores >= C else rounds * arm.cores
     n = dt = nfev = 0
@@ -339,6 +340,7 @@ def run_reference(args):
     arm = CpuArm(kind, args.restarts)
     n = dt = nfev = steps = 0
     # a step = all candidates of a beam while that takes under ~12 s, else a bounded sample of them
+    arm.step(beams[0], limit=arm.cores)                        # imports / first-call costs
     _, t_probe, _ = arm.step(beams[0], limit=arm.cores)
     rounds = max(1, int(12.0 / max(t_probe, 1e-3)))
     limit = None if rounds * arm.cores >= args.cand else rounds * arm.cores
