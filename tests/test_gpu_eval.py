@@ -124,3 +124,41 @@ def test_errors_are_loud(eng):
     bad.insns[0] = isa.encode(isa.OP["VSR_LOAD"], isa.SRC["VSR_SRC_CONST"], 3)  # slot 3 of 1
     with pytest.raises(VsrError):
         eng.set_programs([bad])
+
+
+@pytest.mark.parametrize("n,dtype", [(4999, np.float64), (20011, np.float64), (20011, np.float32)])
+def test_shared_tile_kernel_equals_the_per_pair_kernel(monkeypatch, n, dtype):
+    """vsr_eval / vsr_score over shared tiles (eval_tile_kernel: the points staged once per CTA, every
+    pair run over them -- the path for N >= 5e5) against the per-pair kernel on the same inputs:
+    values, gradients and nan_to_num scores; ragged chunk ends; fp32 and fp64."""
+    X, y = _data(n, seed=3, dtype=dtype)
+    X[:, 4:] = 0.0
+    progs = [compile_skeleton(e, k, VARS) for e, k in SKELETONS]
+    progs = [p for p in progs if p.var_mask < (1 << 4)] * 3
+    assert len(progs) >= 8
+    kmax = max(p.k for p in progs)
+    rng = np.random.RandomState(11)
+    consts = np.zeros((len(progs), kmax))
+    for i, p in enumerate(progs):
+        consts[i, :p.k] = rng.uniform(0.5, 1.5, size=p.k)
+    dt = fitter.F32 if dtype == np.float32 else fitter.F64
+    outs = []
+    for min_points in ("1000000000", "1000"):
+        monkeypatch.setenv("VSR_TILE_MIN_POINTS", min_points)      # read by vsr_create
+        e = fitter.Engine("cuda:0")
+        e.set_points(X, y, dtypes=(dt,), n_vars=4)
+        e.set_programs(progs)
+        n0 = e.launches
+        loss, grad = e.eval(np.arange(len(progs)), consts, dtype=dt, grad=True)
+        score = e.score(np.arange(len(progs)), consts, dtype=dt)
+        outs.append((loss.cpu().numpy(), grad.cpu().numpy(), score.cpu().numpy(), e.launches - n0))
+        e.close()
+    (l0, g0, s0, _), (l1, g1, s1, _) = outs
+    tol = 1e-12 if dtype == np.float64 else 2e-6
+    np.testing.assert_array_equal(np.isnan(l0), np.isnan(l1))
+    ok = np.isfinite(l0)
+    np.testing.assert_allclose(l1[ok], l0[ok], rtol=tol)
+    np.testing.assert_allclose(s1, s0, rtol=tol)
+    fin = np.isfinite(g0) & np.isfinite(g1)
+    np.testing.assert_allclose(g1[fin], g0[fin], rtol=100 * tol, atol=100 * tol * np.abs(g0[fin]).max())
+    np.testing.assert_array_equal(np.isfinite(g0), np.isfinite(g1))

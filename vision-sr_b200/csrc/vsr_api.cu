@@ -106,6 +106,8 @@ struct vsr_handle {
   PinnedBuf h_lists;
   int64_t launches = 0;
   int hook[4] = {0, 0, 0, 0};  // VSR_GEOMETRY measurement hook, read once in vsr_create
+  int tile_smem_kb = 200;            // shared memory of an eval_tile_kernel CTA (fixed part + staged chunk)
+  int64_t tile_min_points = 500000;  // vsr_eval / vsr_score share staged chunks between the pairs from this N on
   int steal_span = 3;          // a launch takes runs of groups up to this many tangent widths narrower
   int latency_k = 0;
   // measurement hooks
@@ -204,6 +206,25 @@ cudaError_t launch_eval(int K, const vsr::EvalArgs& a, int threads, size_t smem,
 #undef C
   }
   return cudaErrorInvalidValue;
+}
+
+template <typename T>
+cudaError_t launch_eval_tile(int K, const vsr::EvalTileArgs& a, size_t smem, cudaStream_t st) {
+  switch (K) {
+#define C(KK) case KK: return vsr::launch_eval_tile_T<T, KK>(a, smem, st);
+    C(0) C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(12) C(16)
+#undef C
+  }
+  return cudaErrorInvalidValue;
+}
+
+int eval_tile_threads_of(int K) {
+  switch (K) {
+#define C(KK) case KK: return vsr::eval_tile_threads<KK>();
+    C(0) C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(12) C(16)
+#undef C
+  }
+  return 512;
 }
 
 int next_pow2(int64_t v) {
@@ -307,10 +328,56 @@ int stage_lists(vsr_handle* h, const std::vector<int32_t>& all, cudaStream_t st)
 int run_eval_group(vsr_handle* h, int K, int dtype, const int32_t* d_prog, const int32_t* d_row,
                    const int32_t* d_out, int n_pairs, int kmax, int max_insn, int max_imm,
                    const double* consts, int kstride, double* out_loss, double* out_grad,
-                   cudaStream_t st, int nan_to_num = 0) {
+                   cudaStream_t st, int nan_to_num = 0, unsigned var_mask = 0) {
   const PointSlot& ps = h->pts[dtype];
   const int P = points_per_thread(K);
   const int64_t N = ps.n;
+  // Large N and several pairs: chunks of the points staged once per CTA and shared by all pairs
+  // (eval_tile_kernel).  The choice is a function of (N, number of pairs, columns) only.
+  if (N >= h->tile_min_points && n_pairs >= 8) {
+    const int elem = dtype == VSR_F64 ? 8 : 4;
+    if (var_mask == 0) var_mask = ps.n_vars >= 32 ? 0xffffffffu : ((1u << ps.n_vars) - 1u);
+    vsr::EvalTileArgs t;
+    t.n_cols = 0;
+    for (int j = 0; j < VSR_MAX_VARS; ++j) t.col_of_var[j] = (((var_mask >> j) & 1u) && j < ps.n_vars) ? t.n_cols++ : -1;
+    const int threads = eval_tile_threads_of(K);
+    const size_t fixed = vsr::eval_tile_fixed_doubles(K, threads, max_insn) * 8;
+    const size_t budget = (size_t)h->tile_smem_kb * 1024;
+    if (fixed + (size_t)(t.n_cols + 1) * 1024 * elem <= budget) {
+      int64_t cap = (int64_t)((budget - fixed) / ((size_t)(t.n_cols + 1) * elem));  // points a CTA can hold
+      cap &= ~(int64_t)127;
+      int64_t chunks = (N + cap - 1) / cap;
+      chunks = (chunks + h->num_sms - 1) / h->num_sms * h->num_sms;  // whole waves of one CTA per SM
+      int64_t chunk = (N + chunks - 1) / chunks;
+      chunk = (chunk + 127) & ~(int64_t)127;
+      chunks = (N + chunk - 1) / chunk;
+      VSR_CUDA(h, h->d_partial.reserve((size_t)n_pairs * chunks * (K + 1) * sizeof(double)));
+      t.e.pt = table_of(h);
+      t.e.pts = points_of(ps);
+      t.e.pair_prog = d_prog;
+      t.e.pair_row = d_row;
+      t.e.pair_out = d_out;
+      t.e.n_pairs = n_pairs;
+      t.e.kstride = kstride;
+      t.e.consts = consts;
+      t.e.partial = (double*)h->d_partial.p;
+      t.e.nsplit = (int)chunks;
+      t.e.nan_to_num = nan_to_num;
+      t.chunk = (int)chunk;
+      t.stride = (int)chunk;
+      t.tma_ok = (((uintptr_t)ps.X % 16 == 0) && ((uintptr_t)ps.y % 16 == 0) && ((ps.ldx * elem) % 16 == 0)) ? 1 : 0;
+      t.max_insn = max_insn;
+      const size_t smem = fixed + (size_t)(t.n_cols + 1) * chunk * elem;
+      cudaError_t e = dtype == VSR_F64 ? launch_eval_tile<double>(K, t, smem, st) : launch_eval_tile<float>(K, t, smem, st);
+      if (e != cudaSuccess) return fail(h, VSR_ECUDA, "eval tile kernel launch failed (smem %zu): %s", smem, cudaGetErrorString(e));
+      const int total = n_pairs * (K + 1);
+      vsr::eval_finalize<<<(total + 127) / 128, 128, 0, st>>>(t.e.partial, d_prog, d_out, t.e.pt.k, n_pairs, (int)chunks, K,
+                                                               kstride, 1.0 / (double)N, out_loss, out_grad);
+      VSR_CUDA(h, cudaGetLastError());
+      h->launches += 2;
+      return VSR_OK;
+    }
+  }
   int threads = 32 * std::min<int64_t>(8, std::max<int64_t>(1, next_pow2((N + 32 * P * 4 - 1) / (32 * P * 4))));
   const int64_t tile = (int64_t)threads * P;
   const int64_t tiles = (N + tile - 1) / tile;
@@ -421,6 +488,8 @@ int vsr_create(int device, vsr_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   if (const char* env = getenv("VSR_GEOMETRY")) sscanf(env, "%d:%d:%d:%d", &h->hook[0], &h->hook[1], &h->hook[2], &h->hook[3]);
   if (const char* env = getenv("VSR_STEAL_SPAN")) h->steal_span = atoi(env);
+  if (const char* env = getenv("VSR_TILE_MIN_POINTS")) h->tile_min_points = atoll(env);  // measurement / test hook
+  if (const char* env = getenv("VSR_TILE_SMEM_KB")) h->tile_smem_kb = std::max(48, std::min(220, atoi(env)));
   if (const char* env = getenv("VSR_LATENCY_K")) h->latency_k = atoi(env);
   // scratch every fit needs, allocated here rather than inside the first fit: run lists (pinned
   // + device), run counters, eval partials, the side streams and their events
@@ -662,8 +731,7 @@ int vsr_eval(vsr_handle* h, const int32_t* prog_idx, const int32_t* const_row, i
     g.kmax = std::max(g.kmax, k);
     g.max_insn = std::max(g.max_insn, h->h_ninsn[c]);
     g.max_imm = std::max(g.max_imm, h->h_nimm[c]);
-    // output row rides in a third list
-    (void)0;
+    g.var_mask |= h->h_varmask[c];
   }
   // lists: for each group prog | row | out
   std::vector<int32_t> all;
@@ -701,7 +769,7 @@ int vsr_eval(vsr_handle* h, const int32_t* prog_idx, const int32_t* const_row, i
     if (!n) continue;
     rc = run_eval_group(h, g.K, dtype, dl + off[gi], dl + off[gi] + n, dl + off[gi] + 2 * n, n,
                         g.kmax, g.max_insn, g.max_imm, consts, kstride, out_loss,
-                        g.K > 0 ? out_grad : nullptr, st);
+                        g.K > 0 ? out_grad : nullptr, st, 0, g.var_mask);
     if (rc) return rc;
   }
   if (out_grad && !toowide.prog.empty()) {
@@ -725,12 +793,14 @@ int vsr_score(vsr_handle* h, const int32_t* prog_idx, const int32_t* const_row, 
   cudaStream_t st = (cudaStream_t)stream;
   VSR_CUDA(h, cudaSetDevice(h->device));
   int kmax = 0, max_insn = 0, max_imm = 0;
+  unsigned var_mask = 0;
   std::vector<int32_t> all;
   for (int p = 0; p < n_pairs; ++p) {
     const int c = prog_idx[p];
     if (c < 0 || c >= h->n_programs) return fail(h, VSR_EINVAL, "pair %d: program %d out of range", p, c);
     if (h->h_k[c] > kstride) return fail(h, VSR_EINVAL, "pair %d: %d constants > kstride %d", p, h->h_k[c], kstride);
     if ((rc = check_vars(h, c, dtype))) return rc;
+    var_mask |= h->h_varmask[c];
     kmax = std::max(kmax, h->h_k[c]);
     max_insn = std::max(max_insn, h->h_ninsn[c]);
     max_imm = std::max(max_imm, h->h_nimm[c]);
@@ -742,7 +812,7 @@ int vsr_score(vsr_handle* h, const int32_t* prog_idx, const int32_t* const_row, 
   if (rc) return rc;
   const int32_t* dl = (const int32_t*)h->d_lists.p;
   return run_eval_group(h, 0, dtype, dl, dl + n_pairs, dl + 2 * n_pairs, n_pairs, kmax, max_insn, max_imm,
-                        consts, kstride, out_mse, nullptr, st, /*nan_to_num=*/1);
+                        consts, kstride, out_mse, nullptr, st, /*nan_to_num=*/1, var_mask);
 }
 
 int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int32_t n_runs,

@@ -76,6 +76,23 @@ cudaError_t launch_eval_T(const EvalArgs& a, int threads, size_t smem, cudaStrea
 }
 
 template <typename T, int K>
+cudaError_t launch_eval_tile_T(const EvalTileArgs& a, size_t smem, cudaStream_t st) {
+  constexpr int P = points_per_thread(K);
+  auto kern = eval_tile_kernel<T, K, P>;
+  static size_t smem_limit[32] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (smem > smem_limit[dev & 31]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_limit[dev & 31] = smem;
+  }
+  kern<<<a.e.nsplit, eval_tile_threads<K>(), smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <typename T, int K>
 cudaError_t preload_T() {
   constexpr int P = points_per_thread(K);
   cudaFuncAttributes attr;
@@ -87,5 +104,6 @@ cudaError_t preload_T() {
 template cudaError_t preload_T<VSR_INST_T, VSR_INST_K>();
 template cudaError_t launch_fit_T<VSR_INST_T, VSR_INST_K>(const FitArgs&, int, int, size_t, int, cudaStream_t);
 template cudaError_t launch_eval_T<VSR_INST_T, VSR_INST_K>(const EvalArgs&, int, size_t, cudaStream_t);
+template cudaError_t launch_eval_tile_T<VSR_INST_T, VSR_INST_K>(const EvalTileArgs&, size_t, cudaStream_t);
 
 }  // namespace vsr

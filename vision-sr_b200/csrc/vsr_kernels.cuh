@@ -325,7 +325,7 @@ struct SlicePoints {
 };
 
 // One pass over the resident slice (cnt points); partial sums parked like sweep_points does.
-template <typename T, int K, int P>
+template <typename T, int K, int P, bool NTN = false>
 __device__ __forceinline__ void sweep_slice(const vsr_insn_t* prog, const double* imm, const T* cst,
                                             const T* xs, const T* ys, int stride, int cnt, double* scratch,
                                             int tid, int nt) {
@@ -351,7 +351,12 @@ __device__ __forceinline__ void sweep_slice(const vsr_insn_t* prog, const double
 #pragma unroll
     for (int p = 0; p < P; ++p) {
       if (src.idx[p] == base + p * nt + tid) {  // valid[p], from the kept index
-        const double r = (double)acc[p].v - (double)ys[src.idx[p]];
+        T pv = acc[p].v;
+        if (NTN) {  // numpy's nan_to_num on the prediction (the drivers' scoring rule, see sweep_points)
+          const T big = sizeof(T) == 8 ? (T)1.7976931348623157e308 : (T)3.4028234663852886e38;
+          pv = pv != pv ? T(0) : (pv > big ? big : (pv < -big ? -big : pv));
+        }
+        const double r = (double)pv - (double)ys[src.idx[p]];
         ps += r * r;
 #pragma unroll
         for (int t = 0; t < K; ++t) {
@@ -1001,6 +1006,125 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalArgs a) {
                           (int)blockDim.x);
   block_totals<K>(red, (int)threadIdx.x, (int)blockDim.x,
                   a.partial + ((int64_t)pair * a.nsplit + split) * (K + 1));
+}
+
+// ---- batched evaluation over SHARED tiles (large N) ------------------------------------------------
+// eval_kernel gives every (pair, split) CTA its own pass over the columns: at N = 1e7 and 1024 pairs
+// the launch requests ~1000x the data set from L2 / HBM.  Here a CTA owns one CHUNK of the points,
+// stages its columns and y ONCE into shared memory (TMA bulk copies, like fit_kernel's resident
+// slices) and then runs EVERY pair over that chunk: the points cross HBM once per launch, whatever
+// the number of pairs.  Partial sums go to partial[pair][chunk][K+1]; eval_finalize adds the chunks
+// in index order (deterministic).
+struct EvalTileArgs {
+  EvalArgs e;        // e.nsplit = number of chunks = gridDim.x
+  int32_t chunk;     // points per CTA (multiple of 32)
+  int32_t stride;    // elements between columns of the staged chunk
+  int32_t n_cols;    // columns staged
+  int32_t tma_ok;
+  int32_t max_insn;  // longest program of the launch (sizes the code area)
+  int32_t col_of_var[VSR_MAX_VARS];
+};
+
+template <int K>
+__host__ __device__ constexpr int eval_tile_threads() {
+  return K <= 2 ? 1024 : 512;
+}
+
+// dynamic shared memory, in doubles: red[(K+1)*threads] | cst[kSeatCstDoubles] | imm[VSR_MAX_IMMS] |
+// insn[max_insn + 1] | chunk ((n_cols + 1) * stride * sizeof(T))
+__host__ __device__ inline size_t eval_tile_fixed_doubles(int K, int threads, int max_insn) {
+  size_t d = (size_t)(K + 1) * threads + kSeatCstDoubles + VSR_MAX_IMMS + max_insn + 1;
+  return (d + 1) & ~(size_t)1;
+}
+
+template <typename T, int K, int P>
+__global__ void __launch_bounds__((eval_tile_threads<K>()), 1) eval_tile_kernel(const EvalTileArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double* red = smem;
+  T* cst = reinterpret_cast<T*>(red + (size_t)(K + 1) * nt);
+  double* s_imm = reinterpret_cast<double*>(cst) + kSeatCstDoubles;
+  vsr_insn_t* s_insn = reinterpret_cast<vsr_insn_t*>(s_imm + VSR_MAX_IMMS);
+  T* ys = reinterpret_cast<T*>(smem + eval_tile_fixed_doubles(K, nt, a.max_insn));
+  T* xs = ys + a.stride;
+  const int64_t N = a.e.pts.n;
+  const int64_t n0 = (int64_t)blockIdx.x * a.chunk;
+  const int cnt = (int)((n0 + a.chunk <= N ? a.chunk : (N > n0 ? N - n0 : 0)));
+  const T* X = static_cast<const T*>(a.e.pts.X);
+  const T* y = static_cast<const T*>(a.e.pts.y);
+  // ---- stage the chunk ----
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  {
+    constexpr int kAlign = 16 / (int)sizeof(T);
+    const int full = cnt & ~(kAlign - 1);
+    const bool use_tma = a.tma_ok && full > 0;
+    if (tid == 0 && use_tma) {
+      const uint32_t bytes = (uint32_t)full * (uint32_t)sizeof(T);
+      mbar_expect_tx(&s_bar, bytes * (uint32_t)(a.n_cols + 1));
+      tma_bulk_load(ys, y + n0, bytes, &s_bar);
+      for (int j = 0; j < VSR_MAX_VARS; ++j)
+        if (a.col_of_var[j] >= 0)
+          tma_bulk_load(xs + (size_t)a.col_of_var[j] * a.stride, X + (int64_t)j * a.e.pts.ldx + n0, bytes, &s_bar);
+    }
+    const int first = use_tma ? full : 0;
+    for (int i = first + tid; i < cnt; i += nt) ys[i] = y[n0 + i];
+    for (int j = 0; j < VSR_MAX_VARS; ++j) {
+      const int sj = a.col_of_var[j];
+      if (sj < 0) continue;
+      for (int i = first + tid; i < cnt; i += nt) xs[(size_t)sj * a.stride + i] = X[(int64_t)j * a.e.pts.ldx + n0 + i];
+    }
+    if (use_tma) mbar_wait(&s_bar, 0);
+    __syncthreads();
+  }
+  // ---- every pair over the staged chunk ----
+  // The program, literals and constants of pair p+1 are FETCHED (global -> registers, one word per
+  // thread: programs have at most VSR_MAX_INSNS <= blockDim words) before the sweep of pair p and
+  // stored to the code area after it, so their L2 latency hides behind the sweep.
+  vsr_insn_t nx_w = 0;
+  double nx_imm = 0.0, nx_c = 0.0;
+  int nx_ni = 0, nx_nm = 0, nx_k = 0;
+  auto fetch = [&](int pair) {
+    const int prog = a.e.pair_prog[pair];
+    nx_k = a.e.pt.k[prog];
+    const int i0 = a.e.pt.insn_off[prog], m0 = a.e.pt.imm_off[prog];
+    nx_ni = a.e.pt.insn_off[prog + 1] - i0;
+    nx_nm = a.e.pt.imm_off[prog + 1] - m0;
+    nx_w = tid < nx_ni ? a.e.pt.insns[i0 + tid] : (vsr_insn_t)0;
+    nx_imm = tid < nx_nm ? a.e.pt.imms[m0 + tid] : 0.0;
+    nx_c = tid < nx_k ? a.e.consts[(int64_t)a.e.pair_row[pair] * a.e.kstride + tid] : 0.0;
+  };
+  auto commit = [&]() {
+    if (tid <= nx_ni) {
+      vsr_insn_t w = 0;  // pad word after END
+      if (tid < nx_ni) {
+        w = nx_w;
+        const unsigned op = VSR_OP(w);
+        if (op >= VSR_LOAD && op <= VSR_RPOW && op != VSR_PUSH && VSR_SRC(w) == VSR_SRC_VAR)
+          w = (w & ~((vsr_insn_t)0xffff << 16)) | ((vsr_insn_t)a.col_of_var[VSR_IDX(w)] << 16);
+        w = predecode(w);
+      }
+      s_insn[tid] = w;
+    }
+    if (tid < nx_nm) s_imm[tid] = nx_imm;
+    if (tid < nx_k) cst[tid] = (T)nx_c;
+  };
+  if (a.e.n_pairs > 0) fetch(0);
+  for (int pair = 0; pair < a.e.n_pairs; ++pair) {
+    commit();
+    __syncthreads();
+    if (pair + 1 < a.e.n_pairs) fetch(pair + 1);
+    if (K == 0 && a.e.nan_to_num)
+      sweep_slice<T, K, P, true>(s_insn, s_imm, cst, xs, ys, a.stride, cnt, red, tid, nt);
+    else
+      sweep_slice<T, K, P>(s_insn, s_imm, cst, xs, ys, a.stride, cnt, red, tid, nt);
+    // (block_totals ends with a barrier over all threads: the code area may be rewritten after it)
+    block_totals<K>(red, tid, nt, a.e.partial + ((int64_t)pair * a.e.nsplit + blockIdx.x) * (K + 1));
+  }
 }
 
 #if defined(VSR_API_TU)  // plain kernels: defined once, in the API translation unit

@@ -19,6 +19,10 @@ cudaError_t launch_fit_T(const FitArgs& a, int threads, int cs, size_t smem, int
 template <typename T, int K>
 cudaError_t launch_eval_T(const EvalArgs& a, int threads, size_t smem, cudaStream_t st);
 
+// eval over shared tiles (large N): one CTA per chunk of the points, see eval_tile_kernel
+template <typename T, int K>
+cudaError_t launch_eval_tile_T(const EvalTileArgs& a, size_t smem, cudaStream_t st);
+
 // forces the (lazily loaded) kernels of one instantiation onto the device
 template <typename T, int K>
 cudaError_t preload_T();
