@@ -67,6 +67,7 @@ std::vector<vsr_insn_t> predecoded(const vsr_insn_t* prog) {
     out.push_back(vsr::predecode(prog[i]));
     if (VSR_OP(prog[i]) == VSR_END) break;
   }
+  out.push_back(0);  // pad word: the interpreter fetches one word ahead
   return out;
 }
 

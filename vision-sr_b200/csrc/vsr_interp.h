@@ -485,12 +485,16 @@ VSR_HD void eval_points(const vsr_insn_t* __restrict__ prog, const double* __res
 #pragma unroll
     for (int i = 0; i < (K > 0 ? K : 1); ++i) acc[p].d[i] = T(0);
   }
-  for (int pc = 0;; ++pc) {
-    const vsr_insn_t w = prog[pc];
+  // the NEXT word is fetched before the current handler runs, so its shared-memory latency hides
+  // behind the handler (every program is followed by a pad word, so the fetch past END is legal)
+  vsr_insn_t w = prog[0];
+  for (int pc = 1;; ++pc) {
+    const unsigned hid = VSR_HANDLER(w);
     const unsigned idx = VSR_IDX(w);
     const unsigned am = VSR_AMASK(w);
     const unsigned bm = VSR_BMASK(w);
-    switch (VSR_HANDLER(w)) {
+    w = prog[pc];  // consumed by the next trip (its latency overlaps the jump-table load)
+    switch (hid) {
       case VSR_H_END:
         return;
       case VSR_H_PUSH:
