@@ -551,6 +551,10 @@ def main():
                 want = 0 if np.all(np.isnan(fm[c])) else int(np.nanargmin(fm[c]))
                 if int(w[c, 1]) != want or not np.array_equal(w[c, 3:3 + lx.shape[2]], lx[c, want], equal_nan=True):
                     bad += 1
+                    if rank == 0:
+                        print(f"sharded != one GPU: beam {beams[mine[i]].name} candidate {c}: restart {int(w[c, 1])} vs {want}, "
+                              f"score {w[c, -1]!r} vs {fm[c, want]!r}, scores of all restarts {fm[c].tolist()}, "
+                              f"lastx {w[c, 3:3 + lx.shape[2]].tolist()} vs {lx[c, want].tolist()}", file=sys.stderr)
         t_bad = torch.tensor([bad], device=dev)
         dist.all_reduce(t_bad)
         shard_check = {"beams_checked": n_chk, "candidates_differing_from_one_gpu": int(t_bad.item())}
