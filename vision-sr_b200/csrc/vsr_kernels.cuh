@@ -668,8 +668,12 @@ __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, Fi
   for (;;) {
     if (my_prog < 0) {  // empty seat: take the next run of the launch
       int r = -1;
-      while (*s_qcur < a.n_queues) {
+      for (;;) {
+        // ONE read per trip: another seat's warp may advance s_qcur at any time, and a second read
+        // could return n_queues -- the counter of a group this launch must not touch (its run would
+        // be skipped by the launch that owns it)
         const int q = *s_qcur;
+        if (q >= a.n_queues) break;
         if (lane == 0) r = atomicAdd(a.queue + q, 1) + a.q_begin[q];
         r = __shfl_sync(0xffffffffu, r, 0);
         if (r < a.q_end[q]) break;
