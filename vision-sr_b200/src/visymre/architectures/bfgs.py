@@ -229,7 +229,9 @@ class _Compiling:
     the host pool (heaviest skeletons first).  ``wait(indices)`` blocks until those candidates are
     compiled; ``out[i]`` is then ``(expr, k, Program)`` or the ``Exception`` candidate i raised."""
 
-    def __init__(self, pred_strs, cfg, test_data, variables):
+    def __init__(self, pred_strs, cfg, test_data, variables, share=None):
+        """``share = (rank, world)``: the ranks of a process group were handed the same beam; each
+        compiles every world-th missing skeleton and ``exchange()`` hands the programs round."""
         self.keys = keys = [_cache_key(t, cfg, test_data, variables) for t in pred_strs]
         self.out = out = [_COMPILED.get(k) for k in keys]
         miss = [i for i, h in enumerate(out) if h is None]
@@ -243,11 +245,17 @@ class _Compiling:
         c_id = next((i for i, w in test_data.id2word.items() if w in ("c", "constant")), 3)
         # weight: constants first (the iteration cap of a run is 200 k, bfgs.py:115), then length
         self.weight = [(sum(1 for t in k[0] if t == c_id), len(k[0])) for k in keys]
-        pool = hostpool.get_pool(_host_workers(cfg)) if len(todo) >= 8 else None
+        todo.sort(key=lambda i: self.weight[i], reverse=True)
+        self.shared = None
+        if share is not None and share[1] > 1 and todo:
+            self.shared = todo                        # what the ranks compile between them (same list everywhere)
+            todo = todo[share[0]::share[1]]
+        self.mine = list(todo)
+        workers = _host_workers(cfg)
+        pool = hostpool.get_pool(workers) if (len(todo) >= 8 and workers >= 2) else None
         if pool is not None:
             # small tasks, heaviest skeletons first: the workers stay evenly loaded to the end and the
             # candidates with the longest fits are ready first
-            todo.sort(key=lambda i: self.weight[i], reverse=True)
             per = max(1, min(4, len(todo) // (3 * hostpool._POOL_N)))
             bits = (bool(_opt(cfg, "add_coefficients_if_not_existing", False)),)
             id2word = dict(test_data.id2word)
@@ -262,12 +270,27 @@ class _Compiling:
                 try:
                     out[i] = _remember(keys[i], compile_tokens(pred_strs[i], cfg, test_data, variables))
                 except Exception as exc:  # noqa: BLE001 -- the wrapper's contract (model.py:15-19)
-                    out[i] = exc
+                    out[i] = hostpool._portable(exc) if self.shared is not None else exc
             self._fill_dups()
 
     @property
     def staged(self):
         return bool(self.pending)
+
+    def exchange(self):
+        """Sharded compilation: one all_gather_object of what each rank compiled."""
+        self.wait(self.mine)
+        if self.shared is not None:
+            import torch.distributed as dist
+            parts = [None] * dist.get_world_size()
+            dist.all_gather_object(parts, [(i, self.out[i]) for i in self.mine])
+            for part in parts:
+                for i, hit in part:
+                    if self.out[i] is None:
+                        self.out[i] = hit if isinstance(hit, Exception) else _remember(self.keys[i], hit)
+            self.shared = None
+        self._fill_dups()
+        return self.out
 
     def _fill_dups(self):
         for i in self.dup:
@@ -427,7 +450,11 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
 
     # ---- Q1-Q5 + compilation, per candidate (failures stay per candidate): started here, collected
     # stage by stage below, while the GPU already fits the candidates that are ready ----
-    comp = _Compiling(pred_strs, cfg, test_data, variables)
+    world = sharding.world_size() if _opt(cfg, "shard", True) and not _opt(cfg, "idx_remove", False) else 1
+    comp = _Compiling(pred_strs, cfg, test_data, variables,
+                      share=(sharding.rank(), world) if world > 1 else None)
+    if world > 1:
+        comp.exchange()
     n_cand = len(pred_strs)
     cands = [None] * n_cand
     if not comp.staged and all(isinstance(h, Exception) for h in comp.out):
@@ -562,11 +589,26 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
         picked[ci] = [best_consts, best_loss, csyms]
         return [i for i, v in enumerate(best_consts) if abs(v) < thr] if c.k > 0 else []
 
-    for ci, rec in win_of.items():
-        k = cands[ci].k
-        small = _pick(ci, rec[3:3 + k].copy(), np.float32(rec[-1]) if score_dtype == fitter.F32 else rec[-1])
-        if small:
-            prune_waits.append((ci, _prepare_prune_async(cands[ci].prog, small, variables, cfg, many=len(win_of) >= 4)))
+    if win_of:
+        # sharded: every rank holds the same winners; the symbolic prune work is dealt over the ranks
+        # and handed round with one all_gather_object
+        todo = []
+        for ci in sorted(win_of):
+            rec, k = win_of[ci], cands[ci].k
+            small = _pick(ci, rec[3:3 + k].copy(), np.float32(rec[-1]) if score_dtype == fitter.F32 else rec[-1])
+            if small:
+                todo.append((ci, small))
+        mine = todo[sharding.rank()::world]
+        waits = [(ci, _prepare_prune_async(cands[ci].prog, small, variables, cfg, many=len(mine) >= 4 and _host_workers(cfg) >= 2))
+                 for ci, small in mine]
+        done = [(ci, wait()) for ci, wait in waits]
+        if world > 1 and todo:
+            import torch.distributed as dist
+            parts = [None] * world
+            dist.all_gather_object(parts, done)
+            done = [item for part in parts for item in part]
+        for ci, got in done:
+            prune_waits.append((ci, (lambda g=got: g)))
     waiting = list(launched)
     while waiting:
         pos = next((j for j, w in enumerate(waiting) if w[3].query()), None)

@@ -29,6 +29,10 @@ def world_size(group=None):
     return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
 
+def rank(group=None):
+    return dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+
+
 def broadcast_from_rank0(t, group=None):
     """Rank 0's copy of ``t`` on every rank (starting points drawn from an unseeded RNG differ
     per process, bfgs.py:103)."""
