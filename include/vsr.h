@@ -154,6 +154,20 @@ int vsr_beam_mask(const int64_t* generated_dev, int64_t ld, int32_t beam, int32_
                   const float* beam_scores_dev, const vsr_beam_rules* rules, int32_t n_words,
                   float* out_mask_dev, void* stream);
 
+/* The same mask, INCREMENTALLY: the decode loop appends one token per beam per step, so the walk's
+ * state (the open frames of the prefix tree) is kept on the device and a step consumes one token per
+ * beam: O(open frames) instead of O(cur_len) per beam per step.  The caller owns the state arrays
+ * (it re-orders their rows when the beam search re-orders the beams) and initialises a fresh beam to
+ * depth = 1, op[0] = -1, missing[0] = 1, cons[0] = 0, pos = 0.
+ *   op, missing [beam][max_depth] int8; cons [beam][max_depth] uint64; depth, pos [beam] int32
+ *   tokens [beam] int64: the token appended to every beam at this step
+ *   out_mask [beam][n_words]: the mask for the NEXT token (what vsr_beam_mask gives for the prefix
+ *   extended by `tokens`); rows of beams with a score below -1e8 are all zero */
+int vsr_beam_mask_step(int8_t* op_dev, int8_t* missing_dev, uint64_t* cons_dev, int32_t* depth_dev,
+                       int32_t* pos_dev, int32_t max_depth, const int64_t* tokens_dev, int32_t beam,
+                       const float* beam_scores_dev, const vsr_beam_rules* rules, int32_t n_words,
+                       float* out_mask_dev, void* stream);
+
 /* Number of kernels this handle has launched since creation (bench.py reports it). */
 int64_t vsr_launch_count(const vsr_handle* h);
 

@@ -110,6 +110,7 @@ struct vsr_handle {
   int64_t tile_min_points = 500000;  // vsr_eval / vsr_score share staged chunks between the pairs from this N on
   int steal_span = 3;          // a launch takes runs of groups up to this many tangent widths narrower
   int latency_k = 0;
+  bool queue_by_candidate = false;
   // measurement hooks
   bool profiling = false;
   long long* phase_cycles = nullptr;  // optional device buffer [n_slots][8], see vsr_set_phase_buffer
@@ -491,6 +492,7 @@ int vsr_create(int device, vsr_handle** out) {
   if (const char* env = getenv("VSR_TILE_MIN_POINTS")) h->tile_min_points = atoll(env);  // measurement / test hook
   if (const char* env = getenv("VSR_TILE_SMEM_KB")) h->tile_smem_kb = std::max(48, std::min(220, atoi(env)));
   if (const char* env = getenv("VSR_LATENCY_K")) h->latency_k = atoi(env);
+  h->queue_by_candidate = getenv("VSR_QUEUE_BY_CANDIDATE") != nullptr;
   // scratch every fit needs, allocated here rather than inside the first fit: run lists (pinned
   // + device), run counters, eval partials, the side streams and their events
   e = h->h_lists.reserve(256 << 10);
@@ -874,7 +876,7 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
   // iteration cap, and the seats of a cluster take consecutive queue entries when the launch starts:
   // candidate-major order put four capped runs into one cluster (each then advances at a quarter of
   // the cluster's sweep rate) while other clusters ran dry.
-  const bool by_candidate = getenv("VSR_QUEUE_BY_CANDIDATE") != nullptr;  // measurement hook: the old order
+  const bool by_candidate = h->queue_by_candidate;  // measurement hook (VSR_QUEUE_BY_CANDIDATE, read once in vsr_create): the old order
   for (auto& g : groups) {
     std::vector<int> order(g.prog.size()), rep(g.prog.size());
     {

@@ -148,6 +148,67 @@ def _bits(ids):
     return m
 
 
+def _beam_rules(n_words, arity_1_ids, arity_2_ids, transcendental_ids, all_op_ids, masked_var_ids, pow_id, c_id,
+                start_id, finish_id, pad_id, length_eq):
+    from ..engine import native
+    return native.BeamRules(arity1=_bits(arity_1_ids), arity2=_bits(arity_2_ids),
+                            transcendental=_bits(transcendental_ids), all_ops=_bits(all_op_ids),
+                            masked_vars=_bits([v for v in (masked_var_ids or ()) if int(v) < n_words]),
+                            pow_id=-1 if pow_id is None else int(pow_id),
+                            c_id=-1 if c_id is None else int(c_id), start_id=int(start_id),
+                            finish_id=-1 if finish_id is None else int(finish_id),
+                            pad_id=-1 if pad_id is None else int(pad_id), length_eq=int(length_eq))
+
+
+class BeamMaskState:
+    """The constraint mask of the beam search kept INCREMENTALLY on the device (``vsr_beam_mask_step``).
+
+    The decode loop of ``fitfunc2`` appends one token per beam per step and re-orders the beams
+    (model.py:412-440); the reference re-walks every prefix from its first token at every step
+    (model.py:385-411).  Here the open frames of every beam's prefix tree live in device tensors:
+    ``step(tokens, beam_scores)`` consumes the step's tokens and returns the ``-inf`` mask for the
+    next one, ``reorder(beam_idx)`` follows the search's re-ordering.  No host synchronisation."""
+
+    MAX_DEPTH = 128      # open frames (the stateless kernel walks with the same cap); prefixes are capped at length_eq <= 100 tokens
+
+    def __init__(self, beam, n_words, device="cuda", **rules):
+        from ..engine import native
+        self.lib = native.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise native.VsrError("BeamMaskState needs a CUDA device (there is no CPU path)")
+        self.beam, self.n_words = int(beam), int(n_words)
+        self.rules = _beam_rules(n_words, **rules)
+        D = self.MAX_DEPTH
+        self.op = torch.full((beam, D), -1, dtype=torch.int8, device=self.device)
+        self.missing = torch.zeros((beam, D), dtype=torch.int8, device=self.device)
+        self.missing[:, 0] = 1
+        self.cons = torch.zeros((beam, D), dtype=torch.int64, device=self.device)
+        self.depth = torch.ones(beam, dtype=torch.int32, device=self.device)
+        self.pos = torch.zeros(beam, dtype=torch.int32, device=self.device)
+
+    def reorder(self, beam_idx):
+        idx = torch.as_tensor(beam_idx, device=self.device, dtype=torch.long)
+        self.op, self.missing, self.cons = self.op[idx].contiguous(), self.missing[idx].contiguous(), self.cons[idx].contiguous()
+        self.depth, self.pos = self.depth[idx].contiguous(), self.pos[idx].contiguous()
+
+    def step(self, tokens, beam_scores):
+        import ctypes
+        from ..engine import native
+        tok = tokens.to(device=self.device, dtype=torch.int64).contiguous()
+        sc = beam_scores.to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty((self.beam, self.n_words), dtype=torch.float32, device=self.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            rc = self.lib.vsr_beam_mask_step(p(self.op), p(self.missing), p(self.cons), p(self.depth), p(self.pos),
+                                             self.MAX_DEPTH, p(tok), self.beam, p(sc), ctypes.byref(self.rules),
+                                             self.n_words, p(out), ctypes.c_void_p(st))
+        if rc != 0:
+            raise native.VsrError(f"vsr_beam_mask_step failed ({rc})")
+        return out
+
+
 def beam_constraint_mask(generated, cur_len, beam_scores, n_words, *, arity_1_ids, arity_2_ids,
                          transcendental_ids, all_op_ids, masked_var_ids, pow_id, c_id, start_id,
                          finish_id, pad_id, length_eq):

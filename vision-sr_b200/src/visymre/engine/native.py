@@ -72,6 +72,8 @@ SIGNATURES = {
                                     vp]),
     "vsr_beam_mask": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, vp,
                                      ctypes.POINTER(BeamRules), ctypes.c_int32, vp, vp]),
+    "vsr_beam_mask_step": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int32, vp, ctypes.c_int32, vp,
+                                          ctypes.POINTER(BeamRules), ctypes.c_int32, vp, vp]),
     "vsr_launch_count": (ctypes.c_int64, [vp]),
     "vsr_set_profiling": (ctypes.c_int, [vp, ctypes.c_int32]),
     "vsr_read_profile": (ctypes.c_int, [vp, c_f64p]),
