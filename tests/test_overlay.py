@@ -38,6 +38,10 @@ def test_overlay_patches_fitfunc2_and_the_drivers_module_imports(tmp_path):
     assert "class Model(pl.LightningModule)" in text and "ProcessPoolExecutor(20)" not in text
     with pytest.raises(ValueError):
         overlay.patch_model_source(text)          # a second application finds no marker
+    # the constraint block: a device branch in front of the reference's own (re-indented) statements
+    assert "if generated.is_cuda:" in text and "beam_constraint_mask(" in text
+    assert "hyp_seq = generated[i, :cur_len].cpu().tolist()" in text
+    compile(text, "patched model.py", "exec")
 
     got = _run(tree, True, str(tmp_path / "patched.json"))
     ref = _run(REF, False, str(tmp_path / "reference.json"))

@@ -14,8 +14,11 @@ is first copied there and the copy is patched):
   architectures/model.py  PATCHED  the "BFGS Parallel Part" of ``Model.fitfunc2``
                                    (reference model.py:444-520: 20 worker processes, one
                                    ``bfgs_wrapper`` task per candidate) becomes one call of
-                                   ``refine_hypotheses``; the network, the beam loop and everything
-                                   above line 444 stay the reference's own code
+                                   ``refine_hypotheses``; the "Constraint Logic" block of the beam loop
+                                   (model.py:382-411) gets a device branch (``beam_constraint_mask``,
+                                   one launch per decode step) in front of its own host loop, which
+                                   stays for CPU tensors; the network and the rest of the beam loop
+                                   stay the reference's own code
   scoring.py, hlsc_batch.py added  driver-side scoring / batched HLSC evaluation (optional)
 
 The reference's drivers (``scripts/*_test.py`` through ``scripts/visymre_utils.py``) then run
@@ -53,6 +56,36 @@ def patch_model_source(text):
     return "\n".join(lines[:a] + [indent + l for l in PATCH] + lines[b + 1:])
 
 
+MASK_BEGIN = "# --- Constraint Logic ---"
+MASK_END = "scores = scores + logit_mask"
+
+
+def patch_constraint_block(text):
+    """The "Constraint Logic" block of the beam loop (reference model.py:382-411: every beam copied to the
+    host and walked in Python at every decode step) gets a device branch: one ``vsr_beam_mask`` launch
+    when the beams live on the GPU.  The reference's own statements stay, unchanged, as the branch for
+    CPU tensors.  Mechanical: from the block's marker comment to the line that applies the mask."""
+    lines = text.split("\n")
+    a = next((i for i, l in enumerate(lines) if MASK_BEGIN in l), None)
+    if a is None:
+        raise ValueError("marker %r not found" % MASK_BEGIN)
+    b = next(i for i in range(a, len(lines)) if lines[i].strip() == MASK_END)
+    ind = re.match(r"\s*", lines[a]).group(0)
+    head = [
+        ind + "# --- Constraint Logic --- (vision-sr_b200 overlay: one device launch when the beams are on the GPU)",
+        ind + "if generated.is_cuda:",
+        ind + "    from .refine import beam_constraint_mask",
+        ind + "    logit_mask = beam_constraint_mask(",
+        ind + "        generated, int(cur_len), beam_scores, n_words, arity_1_ids=arity_1_ids, arity_2_ids=arity_2_ids,",
+        ind + "        transcendental_ids=transcendental_ids, all_op_ids=all_op_ids, masked_var_ids=masked_var_ids,",
+        ind + "        pow_id=pow_id, c_id=c_id, start_id=start_id, finish_id=finish_id, pad_id=pad_id,",
+        ind + "        length_eq=self.cfg.length_eq)",
+        ind + "else:",
+    ]
+    body = ["    " + l if l.strip() else l for l in lines[a + 1:b]]
+    return "\n".join(lines[:a] + head + body + lines[b:])
+
+
 def install(checkout, out=None):
     src = os.path.join(checkout, "src", "visymre")
     if not os.path.isfile(os.path.join(src, "architectures", "model.py")):
@@ -78,7 +111,7 @@ def install(checkout, out=None):
     # Model.fitfunc2
     mp = os.path.join(src, "architectures", "model.py")
     with open(mp) as fh:
-        patched = patch_model_source(fh.read())
+        patched = patch_constraint_block(patch_model_source(fh.read()))
     with open(mp, "w") as fh:
         fh.write(patched)
     return src
