@@ -32,9 +32,13 @@ def _oracle(job):
     try:
         out = vectorised.bfgs(tokens, X[None], y, cfg, td, x0=x0, record=rec)
     except Exception as exc:  # noqa: BLE001
-        if "complex" in str(exc).lower():
-            # the reference carries complex numbers on (scipy accepts them); the oracle's own float()
-            # refuses them: the reference's complex-sub-tree artefact, not a dropped candidate
+        if "complex" in str(exc).lower() or isinstance(exc, OverflowError):
+            # complex: the reference carries complex numbers on (scipy accepts them), the oracle's own
+            # float() refuses them -- the complex-sub-tree artefact.  OverflowError ("too many digits
+            # in integer"): sympy evaluates exp(<huge>) EXACTLY while the constants of SOME restart are
+            # substituted into the expression (bfgs.py:120-124); the reference crashes there and its
+            # wrapper drops the whole candidate, whatever its other restarts found.  The drop-in prints
+            # only the winner, lazily, and keeps the candidate: a crash of the reference, not a result
             return None, False, [], False
         return None, True, [], True
     st = [r.get("status") for r in rec.restarts[:R]]
