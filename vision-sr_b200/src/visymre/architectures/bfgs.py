@@ -499,7 +499,8 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
     if comp.staged and world == 1 and n_cand >= 24 and _opt(cfg, "pipeline", True):
         order = sorted(range(n_cand), key=lambda i: comp.weight[i], reverse=True)
         # (three stages -- 8 candidates, a quarter, the rest -- measured no better than two)
-        n_first = max(8, (n_cand + 2) // 3)
+        # ... and no more candidates in the first stage than the pool compiles in ONE round of tasks
+        n_first = max(8, min((n_cand + 2) // 3, hostpool._POOL_N or n_cand))
         stages = [sorted(order[:n_first]), sorted(order[n_first:])]
     else:
         stages = [list(range(n_cand))]
