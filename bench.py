@@ -75,7 +75,7 @@ def parse():
     ap.add_argument("--mode", default="auto", choices=["auto", "sharded", "replicas"],
                     help="N > 1: one beam sharded over the ranks (auto) or independent replica beams")
     ap.add_argument("--warps", type=int, default=0)
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=25.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-api", action="store_true", help="skip the refine_hypotheses end-to-end loop")
     ap.add_argument("--rows", default="", help="comma separated table row names (default: table order)")
@@ -314,14 +314,23 @@ def cpu_baseline(beams, args, budget_s):
     n = dt = nfev = 0
     t_all = time.time()
     used = 0
+    # whole beams spread EVENLY over the timed ones (a beam's CPU time varies 10x with its candidates;
+    # the first few are not representative): as many as the budget is expected to cover
+    seen, distinct = set(), []
     for b in beams:
+        if id(b) not in seen:
+            seen.add(id(b))
+            distinct.append(b)
+    want = 1 if limit is not None else max(1, min(len(distinct), int(budget_s / max(t_probe * -(-C // arm.cores), 1e-3))))
+    picks = [distinct[int(round(i * (len(distinct) - 1) / max(1, want - 1)))] for i in range(want)] if want > 1 else distinct[:1]
+    for b in picks:
         a, d, f = arm.step(b, limit=limit)
         n, dt, nfev, used = n + a, dt + d, nfev + f, used + 1
-        if limit is not None or time.time() - t_all + d > budget_s:
+        if limit is not None or time.time() - t_all > 2.0 * budget_s:
             break
     arm.close()
     N = beams[0].X.shape[0]
-    what = (f"all {C} candidates of the first {used} timed beams" if limit is None
+    what = (f"all {C} candidates of {used} of the timed beams (evenly spread)" if limit is None
             else f"the first {limit} of the {C} candidates of the first timed beam")
     return {"value": n / dt, "unit": "candidate-fits/s", "cores": arm.cores, "kind": kind,
             "sample": f"{what} (R={args.restarts}, N={N}), "
