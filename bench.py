@@ -321,12 +321,16 @@ def cpu_baseline(beams, args, budget_s):
         if id(b) not in seen:
             seen.add(id(b))
             distinct.append(b)
-    want = 1 if limit is not None else max(1, min(len(distinct), int(budget_s / max(t_probe * -(-C // arm.cores), 1e-3))))
-    picks = [distinct[int(round(i * (len(distinct) - 1) / max(1, want - 1)))] for i in range(want)] if want > 1 else distinct[:1]
-    for b in picks:
-        a, d, f = arm.step(b, limit=limit)
+    # visiting order: first, last, middle, quarters, ... so that wherever the budget ends the sample is spread
+    order, step = [0, len(distinct) - 1], len(distinct) - 1
+    while step > 1:
+        step = (step + 1) // 2
+        order += [i for i in range(step, len(distinct) - 1, step) if i not in order]
+    order = [i for i in dict.fromkeys(order) if 0 <= i < len(distinct)]
+    for i in order:
+        a, d, f = arm.step(distinct[i], limit=limit)
         n, dt, nfev, used = n + a, dt + d, nfev + f, used + 1
-        if limit is not None or time.time() - t_all > 2.0 * budget_s:
+        if limit is not None or time.time() - t_all + d > budget_s:
             break
     arm.close()
     N = beams[0].X.shape[0]
