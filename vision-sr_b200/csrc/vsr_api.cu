@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "../../include/vsr.h"
@@ -85,8 +86,28 @@ struct PointSlot {
 
 }  // namespace
 
+// Side streams of the width-group launches: ONE pool per device, shared by the handles.  Every handle
+// used to own eight streams; a process with many handles (bench.py keeps one per resident beam) then
+// holds hundreds, which alias on the device's hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default
+// and 32 at most): two launches of one fit landing in the same queue run one AFTER the other, and with
+// persistent kernels the group tails add up (one beam of the bench: 65-75 ms alone, 95-160 ms in the
+// bench process).  A handle takes a window of the pool at an offset of its own, so two handles fitting
+// at the same time (refine_hypotheses stages a beam over two) do not meet.
+constexpr int kPoolStreams = 24;
+constexpr int kHandleStride = 11;
+struct StreamPool {
+  std::mutex mu;
+  std::vector<cudaStream_t> streams;  // created on first use, never destroyed (process lifetime)
+  int next_base = 0;
+};
+StreamPool& pool_of(int device) {
+  static StreamPool pools[64];
+  return pools[device & 63];
+}
+
 struct vsr_handle {
   int device = 0;
+  int stream_base = 0;  // this handle's window of the device's side-stream pool
   int num_sms = 148;
   std::string err;
   PointSlot pts[2];
@@ -499,14 +520,22 @@ int vsr_create(int device, vsr_handle** out) {
   if (e == cudaSuccess) e = h->d_lists.reserve(256 << 10);
   if (e == cudaSuccess) e = h->d_queue.reserve(64 * sizeof(int32_t));
   if (e == cudaSuccess) e = h->d_partial.reserve(1 << 20);
-  for (int i = 0; i < 8 && e == cudaSuccess; ++i) {
-    cudaStream_t s2;
-    e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
-    if (e != cudaSuccess) break;
-    h->side_streams.push_back(s2);
-    cudaEvent_t e2;
-    e = cudaEventCreateWithFlags(&e2, cudaEventDisableTiming);
-    if (e == cudaSuccess) h->ev_join.push_back(e2);
+  {
+    StreamPool& sp = pool_of(device);
+    std::lock_guard<std::mutex> lock(sp.mu);
+    while ((int)sp.streams.size() < kPoolStreams && e == cudaSuccess) {
+      cudaStream_t s2;
+      e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+      if (e == cudaSuccess) sp.streams.push_back(s2);
+    }
+    h->stream_base = sp.next_base;
+    sp.next_base = (sp.next_base + kHandleStride) % kPoolStreams;
+    for (int i = 0; i < kHandleStride && e == cudaSuccess; ++i) {
+      h->side_streams.push_back(sp.streams[(h->stream_base + i) % kPoolStreams]);
+      cudaEvent_t e2;
+      e = cudaEventCreateWithFlags(&e2, cudaEventDisableTiming);
+      if (e == cudaSuccess) h->ev_join.push_back(e2);
+    }
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   if (e != cudaSuccess) {
@@ -535,8 +564,7 @@ void vsr_destroy(vsr_handle* h) {
   h->d_stage.release();
   h->d_queue.release();
   h->h_lists.release();
-  for (auto s2 : h->side_streams) cudaStreamDestroy(s2);
-  for (auto e2 : h->ev_join) cudaEventDestroy(e2);
+  for (auto e2 : h->ev_join) cudaEventDestroy(e2);  // (the side streams belong to the device's pool)
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (auto& sp : h->spans) {
     if (sp.kind == 0) h->event_pool.push_back(sp.a);
@@ -949,14 +977,7 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
   // groups run concurrently: group 0 on the caller's stream, the others on side streams
   // forked from / joined to it with events
   const size_t n_side = groups.size() > 1 ? groups.size() - 1 : 0;
-  while (h->side_streams.size() < n_side) {
-    cudaStream_t s2;
-    VSR_CUDA(h, cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-    h->side_streams.push_back(s2);
-    cudaEvent_t e2;
-    VSR_CUDA(h, cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-    h->ev_join.push_back(e2);
-  }
+  if (n_side > h->side_streams.size()) return fail(h, VSR_EINVAL, "%zu launch groups exceed the side streams", n_side + 1);
   if (n_side && !h->ev_fork) VSR_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   if (n_side) VSR_CUDA(h, cudaEventRecord(h->ev_fork, st));
   for (size_t gi = 0; gi < groups.size(); ++gi) {

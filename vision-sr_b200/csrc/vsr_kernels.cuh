@@ -730,7 +730,8 @@ __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, Fi
       info[0] = S.status;
       info[1] = S.it;
       info[2] = S.nfev;
-      info[3] = 0;
+      // with the phase buffer on (probes): the cluster that ran it; otherwise reserved (0)
+      info[3] = a.phase_cycles != nullptr ? (int32_t)(blockIdx.x / (unsigned)cs) : 0;
       if (timing) {
         const long long now = clock64();
         book.t_logic += now - ta;
