@@ -91,10 +91,11 @@ struct PointSlot {
 // holds hundreds, which alias on the device's hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default
 // and 32 at most): two launches of one fit landing in the same queue run one AFTER the other, and with
 // persistent kernels the group tails add up (one beam of the bench: 65-75 ms alone, 95-160 ms in the
-// bench process).  A handle takes a window of the pool at an offset of its own, so two handles fitting
-// at the same time (refine_hypotheses stages a beam over two) do not meet.
-constexpr int kPoolStreams = 24;
-constexpr int kHandleStride = 11;
+// bench process).  A handle takes a window of the pool at an offset of its own, so the handles that fit
+// at the same time (refine_hypotheses stages a beam over up to four) do not meet.
+constexpr int kPoolStreams = 32;
+constexpr int kHandleStride = 8;   // side streams per handle (+ the caller's stream: nine groups at once; more groups share)
+constexpr int kMaxGroups = 16;
 struct StreamPool {
   std::mutex mu;
   std::vector<cudaStream_t> streams;  // created on first use, never destroyed (process lifetime)
@@ -530,8 +531,8 @@ int vsr_create(int device, vsr_handle** out) {
     }
     h->stream_base = sp.next_base;
     sp.next_base = (sp.next_base + kHandleStride) % kPoolStreams;
-    for (int i = 0; i < kHandleStride && e == cudaSuccess; ++i) {
-      h->side_streams.push_back(sp.streams[(h->stream_base + i) % kPoolStreams]);
+    for (int i = 0; i < kHandleStride; ++i) h->side_streams.push_back(sp.streams[(h->stream_base + i) % kPoolStreams]);
+    for (int i = 0; i < kMaxGroups && e == cudaSuccess; ++i) {
       cudaEvent_t e2;
       e = cudaEventCreateWithFlags(&e2, cudaEventDisableTiming);
       if (e == cudaSuccess) h->ev_join.push_back(e2);
@@ -977,13 +978,13 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
   // groups run concurrently: group 0 on the caller's stream, the others on side streams
   // forked from / joined to it with events
   const size_t n_side = groups.size() > 1 ? groups.size() - 1 : 0;
-  if (n_side > h->side_streams.size()) return fail(h, VSR_EINVAL, "%zu launch groups exceed the side streams", n_side + 1);
+  if (n_side > h->ev_join.size()) return fail(h, VSR_EINVAL, "%zu launch groups: too many", n_side + 1);
   if (n_side && !h->ev_fork) VSR_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   if (n_side) VSR_CUDA(h, cudaEventRecord(h->ev_fork, st));
   for (size_t gi = 0; gi < groups.size(); ++gi) {
     Group& g = groups[gi];
     const int n = (int)g.prog.size();
-    cudaStream_t gs = gi == 0 ? st : h->side_streams[gi - 1];
+    cudaStream_t gs = gi == 0 ? st : h->side_streams[(gi - 1) % h->side_streams.size()];
     if (gi > 0) VSR_CUDA(h, cudaStreamWaitEvent(gs, h->ev_fork, 0));
     vsr::FitArgs a;
     a.pt = table_of(h);

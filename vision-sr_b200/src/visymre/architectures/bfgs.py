@@ -277,6 +277,24 @@ class _Compiling:
     def staged(self):
         return bool(self.pending)
 
+    def ready(self, indices):
+        """The candidates of ``indices`` that are compiled by now (does not block)."""
+        out = []
+        for i in indices:
+            if self.out[i] is not None:
+                out.append(i)
+                continue
+            j = self.first.get(self.keys[i], i)
+            pos = self.owner.get(j)
+            if pos is None:
+                if self.out[j] is not None:
+                    out.append(i)
+                continue
+            fut = self.pending[pos][0]
+            if fut is None or fut.done():
+                out.append(i)
+        return out
+
     def exchange(self):
         """Sharded compilation: one all_gather_object of what each rank compiled."""
         self.wait(self.mine)
@@ -493,17 +511,36 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
     _mark("upload")
 
     world = sharding.world_size() if _opt(cfg, "shard", True) and not rows_removed else 1
-    # Stages: the candidates with the most constants (longest fits; their skeletons are compiled
-    # first) are fitted as soon as THEY are compiled, on the main engine; the rest follows on a side
-    # engine and stream that shares the points.  One stage when there is nothing to overlap.
-    if comp.staged and world == 1 and n_cand >= 24 and _opt(cfg, "pipeline", True):
-        order = sorted(range(n_cand), key=lambda i: comp.weight[i], reverse=True)
-        # (three stages -- 8 candidates, a quarter, the rest -- measured no better than two)
-        # ... and no more candidates in the first stage than the pool compiles in ONE round of tasks
+    # Stages: the skeletons are compiled heaviest first (most constants = longest fits); the fit of a
+    # FIRST stage starts as soon as enough candidates to fill the GPU are compiled -- whichever they
+    # are: sympy takes 3 ms for most skeletons and 30-60 ms for a few -- on the main engine; the rest
+    # follows on side engines and streams that share the points, stragglers in a stage of their own.
+    # One stage when there is nothing to overlap.
+    def _stages():
+        if not (comp.staged and world == 1 and n_cand >= 24 and _opt(cfg, "pipeline", True)):
+            yield list(range(n_cand))
+            return
+        remaining = set(range(n_cand))
         n_first = max(8, min((n_cand + 2) // 3, hostpool._POOL_N or n_cand))
-        stages = [sorted(order[:n_first]), sorted(order[n_first:])]
-    else:
-        stages = [list(range(n_cand))]
+        stage_no, t_last = 0, _time.perf_counter()
+        while remaining:
+            ready = comp.ready(remaining)
+            now = _time.perf_counter()
+            go = len(ready) == len(remaining)
+            if not go and stage_no == 0:
+                go = len(ready) >= n_first
+            elif not go and stage_no < 3:
+                # a later stage goes when most of the rest is there and the stragglers keep it waiting
+                go = len(ready) >= max(8, (3 * len(remaining)) // 4) and now - t_last > 4e-3
+            if go and stage_no == 3:
+                go = len(ready) == len(remaining)      # the last engine takes all that is left
+            if not go:
+                _time.sleep(2e-4)
+                continue
+            stage = sorted(ready)
+            remaining.difference_update(stage)
+            stage_no, t_last = stage_no + 1, now
+            yield stage
 
     def _collect(stage):
         comp.wait(stage)
@@ -534,7 +571,7 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
     fitted = {}     # candidate -> (lastx rows [R, k], final scores [R])   (one GPU)
     win_of = {}     # candidate -> record of the all-gather                (sharded)
     launched = []
-    for si, stage in enumerate(stages):
+    for si, stage in enumerate(_stages()):
         live_s = _collect(stage)
         _mark("compile")
         if not live_s:
