@@ -133,6 +133,7 @@ struct vsr_handle {
   int steal_span = 3;          // a launch takes runs of groups up to this many tangent widths narrower
   int latency_k = 0;
   bool queue_by_candidate = false;
+  int hold_passes = 500;       // see FitArgs::hold_passes (VSR_HOLD_PASSES; 0 / 200 / 500 / 1000: 1044-1077 / 1040-1093 / 1011-1029 / 1028-1053 ms over 27 beams)
   // measurement hooks
   bool profiling = false;
   long long* phase_cycles = nullptr;  // optional device buffer [n_slots][8], see vsr_set_phase_buffer
@@ -515,6 +516,7 @@ int vsr_create(int device, vsr_handle** out) {
   if (const char* env = getenv("VSR_TILE_SMEM_KB")) h->tile_smem_kb = std::max(48, std::min(220, atoi(env)));
   if (const char* env = getenv("VSR_LATENCY_K")) h->latency_k = atoi(env);
   h->queue_by_candidate = getenv("VSR_QUEUE_BY_CANDIDATE") != nullptr;
+  if (const char* env = getenv("VSR_HOLD_PASSES")) h->hold_passes = atoi(env);
   // scratch every fit needs, allocated here rather than inside the first fit: run lists (pinned
   // + device), run counters, eval partials, the side streams and their events
   e = h->h_lists.reserve(256 << 10);
@@ -1036,6 +1038,7 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
       geo.smem = vsr::fit_smem_bytes(geo.seats, g.kmax, g.K, geo.threads / 32, geo.cs, g.max_insn, -1, 0, elem);
     }
     a.phase_cycles = h->phase_cycles;
+    a.hold_passes = h->hold_passes;
     a.resident = geo.resident;
     a.tma_ok = tma_ok ? 1 : 0;
     a.slice_stride = geo.stride;

@@ -77,6 +77,8 @@ struct FitArgs {
   int32_t kmax, max_insn, max_imm;  // maxima over this launch's programs (size the seat areas)
   int32_t n_cols;                   // columns of X this launch's programs read
   int32_t col_of_var[VSR_MAX_VARS]; // slice column of variable j (-1: unused)
+  int32_t hold_passes;      // a seat retires instead of taking a run while two other seats of its cluster hold
+                            // runs with at least this many passes behind them (0: never)
   int32_t* queue;           // [n_queues] next run of each queue, relative to q_begin (zeroed by the host)
   long long* phase_cycles;  // optional [n_slots][8]: cycles of the run's optimiser lane 0: [0] optimiser turns
                             // ([1] taking in the totals, [2] the BFGS step, [4] publishing the request),
@@ -626,7 +628,7 @@ __device__ __forceinline__ void publish_request(const FitArgs& a, int cs, int la
 template <typename T, int K>
 __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, FitState& S, double* ws,
                                           const double* cred, SeatBook& book, volatile int* s_qcur, uint64_t* part_bar,
-                                          uint32_t ctrl_addr, uint32_t req_bar_addr) {
+                                          uint32_t ctrl_addr, uint32_t req_bar_addr, const SeatBook* books, int* s_open) {
   constexpr int W = fit_lanes<K>();
   const bool timing = a.phase_cycles != nullptr && lane == 0;
   long long ta = timing ? clock64() : 0;
@@ -668,6 +670,25 @@ __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, Fi
   for (;;) {
     if (my_prog < 0) {  // empty seat: take the next run of the launch
       int r = -1;
+      // ... unless the cluster already carries two OLD runs (on their way to the iteration cap: each
+      // advances at the cluster's sweep rate divided by its live seats, and the launch ends when the
+      // slowest of them does): then this seat retires and the run goes to a cluster with room.  Two
+      // seats of every cluster always stay open, so the queues drain whatever the rule decides.
+      if (a.hold_passes > 0) {
+        int hold = 0;
+        if (lane == 0) {
+          int n_old = 0;
+          for (int g2 = 0; g2 < a.seats; ++g2)
+            if (&books[g2] != &book && books[g2].prog >= 0 && books[g2].n_pass >= a.hold_passes) ++n_old;
+          if (n_old >= 2) {
+            if (atomicSub(s_open, 1) > 2)
+              hold = 1;
+            else
+              atomicAdd(s_open, 1);
+          }
+        }
+        if (__shfl_sync(0xffffffffu, hold, 0)) break;
+      }
       for (;;) {
         // ONE read per trip: another seat's warp may advance s_qcur at any time, and a second read
         // could return n_queues -- the counter of a group this launch must not touch (its run would
@@ -775,6 +796,7 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   __shared__ __align__(8) uint64_t s_bar;                  // TMA staging of the slice
   __shared__ int s_ticket[kMaxSeats];                      // sweeper warps of this CTA that finished seat g's requests
   __shared__ int s_qcur;  // first queue of this launch that is not drained yet
+  __shared__ int s_open;  // seats of this cluster that still take runs (leader CTA)
 
   const int cs = (int)cluster.num_blocks();
   const int crank = (int)cluster.block_rank();
@@ -814,6 +836,7 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
     mbar_init(&s_bar, 1);
     mbar_fence_init();
     s_qcur = 0;
+    s_open = a.seats;
   }
   if (tid < kMaxSeats) {
     s_book[tid].prog = -1;
@@ -893,7 +916,7 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
         double* seat = VSR_SEAT_STATE(g);
         const bool open = seat_turn<T, K>(a, lane, cs, *reinterpret_cast<FitState*>(seat), seat + kFitStateDoubles,
                                           seat + a.off_cred, s_book[g], &s_qcur, &s_part_bar[g],
-                                          ctrl0 + 8u * (uint32_t)(g * seat_d), smem_u32(&s_req_bar[g]));
+                                          ctrl0 + 8u * (uint32_t)(g * seat_d), smem_u32(&s_req_bar[g]), s_book, &s_open);
         if (open)
           opt_wait |= 1u << g;
         else
