@@ -125,6 +125,7 @@ struct vsr_handle {
   DevBuf d_partial;  // eval partial sums
   DevBuf d_stage;    // device staging of the *_host entry points
   DevBuf d_queue;    // one run counter per launch group (persistent clusters pull runs from it)
+  DevBuf d_handover; // hand-over boards of the launch groups (vsr::Handover)
   PinnedBuf h_lists;
   int64_t launches = 0;
   int hook[4] = {0, 0, 0, 0};  // VSR_GEOMETRY measurement hook, read once in vsr_create
@@ -133,6 +134,7 @@ struct vsr_handle {
   int steal_span = 3;          // a launch takes runs of groups up to this many tangent widths narrower
   int latency_k = 0;
   bool queue_by_candidate = false;
+  bool handover = true;        // run hand-over to clusters that ran dry (VSR_HANDOVER=0: off)
   int hold_passes = 500;       // see FitArgs::hold_passes (VSR_HOLD_PASSES; 0 / 200 / 500 / 1000: 1044-1077 / 1040-1093 / 1011-1029 / 1028-1053 ms over 27 beams)
   // measurement hooks
   bool profiling = false;
@@ -517,6 +519,7 @@ int vsr_create(int device, vsr_handle** out) {
   if (const char* env = getenv("VSR_LATENCY_K")) h->latency_k = atoi(env);
   h->queue_by_candidate = getenv("VSR_QUEUE_BY_CANDIDATE") != nullptr;
   if (const char* env = getenv("VSR_HOLD_PASSES")) h->hold_passes = atoi(env);
+  if (const char* env = getenv("VSR_HANDOVER")) h->handover = atoi(env) != 0;
   // scratch every fit needs, allocated here rather than inside the first fit: run lists (pinned
   // + device), run counters, eval partials, the side streams and their events
   e = h->h_lists.reserve(256 << 10);
@@ -566,6 +569,7 @@ void vsr_destroy(vsr_handle* h) {
   h->d_partial.release();
   h->d_stage.release();
   h->d_queue.release();
+  h->d_handover.release();
   h->h_lists.release();
   for (auto e2 : h->ev_join) cudaEventDestroy(e2);  // (the side streams belong to the device's pool)
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -974,6 +978,17 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
   // one run counter per group: the persistent clusters of a launch pull their runs from it
   VSR_CUDA(h, h->d_queue.reserve(groups.size() * sizeof(int32_t)));
   VSR_CUDA(h, cudaMemsetAsync(h->d_queue.p, 0, groups.size() * sizeof(int32_t), st));
+  // hand-over boards: one per group, sized for the group's widest run
+  std::vector<size_t> ho_off(groups.size() + 1, 0);
+  std::vector<int> ho_slot_d(groups.size(), 0);
+  if (h->handover) {
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+      ho_slot_d[gi] = (vsr::kHandoverHead + vsr::kFitStateDoubles + vsr::fit_workspace_doubles(std::max(1, groups[gi].kmax)) + 1) & ~1;
+      ho_off[gi + 1] = ho_off[gi] + 16 + (size_t)vsr::kHandoverSlots * ho_slot_d[gi] * sizeof(double);
+    }
+    VSR_CUDA(h, h->d_handover.reserve(ho_off.back()));
+    VSR_CUDA(h, cudaMemsetAsync(h->d_handover.p, 0, ho_off.back(), st));
+  }
   // measurement hook: VSR_GEOMETRY="cluster:threads:seats[:optimiser warps]" overrides the launch geometry
   const int hook_cluster = h->hook[0], hook_threads = h->hook[1], hook_seats = h->hook[2], hook_reserved = h->hook[3];
 
@@ -1039,6 +1054,8 @@ int vsr_fit(vsr_handle* h, const int32_t* run_prog, const int32_t* run_slot, int
     }
     a.phase_cycles = h->phase_cycles;
     a.hold_passes = h->hold_passes;
+    a.handover = (h->handover && g.kmax > 0) ? (vsr::Handover*)((char*)h->d_handover.p + ho_off[gi]) : nullptr;
+    a.handover_slot_d = ho_slot_d[gi];
     a.resident = geo.resident;
     a.tma_ok = tma_ok ? 1 : 0;
     a.slice_stride = geo.stride;

@@ -44,6 +44,26 @@ struct Points {
   int64_t ldx;
 };
 
+// ---- hand-over of runs between the clusters of a launch ----------------------------------------------
+// When the launch's queues have drained, the clusters that run dry would exit while others still
+// carry several long runs each, which share their cluster's sweeps.  Instead, the last seat of a
+// cluster to run dry takes a TICKET and waits; a cluster with two or more runs in flight answers a
+// ticket by handing one of its runs over: the optimiser state goes through global memory into the
+// ticket's slot, the run continues in the waiting cluster (the slices are the same in every cluster
+// of a launch, and a run's result does not depend on where it runs).  `live` counts the runs that are
+// seated or being pulled; the waiting clusters leave when it reaches zero with the queues drained.
+constexpr int kHandoverSlots = 64;       // tickets per launch (a waiting cluster takes one at a time)
+constexpr unsigned long long kHandoverWaitNs = 300000ull;  // how long a dry cluster waits for a run
+constexpr int kHandoverHead = 4;         // doubles in front of a slot's state: (flag, slot) (prog, k) t0 n_pass
+struct Handover {
+  int32_t requests;                       // tickets taken by waiting clusters
+  int32_t offers;                         // tickets answered (claimed by CAS: offers < requests)
+  int32_t live;                           // runs seated or being pulled
+  int32_t pad;
+  double slots[1];                        // kHandoverSlots slots of FitArgs::handover_slot_d doubles:
+                                          // head | FitState (kFitStateDoubles) | workspace
+};
+
 constexpr int kMaxSeats = 8;  // runs a cluster can work on at a time
 constexpr int kMaxQueues = 4;  // run queues a launch pulls from: its own and up to three narrower groups'
 
@@ -79,6 +99,8 @@ struct FitArgs {
   int32_t col_of_var[VSR_MAX_VARS]; // slice column of variable j (-1: unused)
   int32_t hold_passes;      // a seat retires instead of taking a run while two other seats of its cluster hold
                             // runs with at least this many passes behind them (0: never)
+  Handover* handover;       // run hand-over between this launch's clusters (nullptr: off)
+  int32_t handover_slot_d;  // doubles per hand-over slot
   int32_t* queue;           // [n_queues] next run of each queue, relative to q_begin (zeroed by the host)
   long long* phase_cycles;  // optional [n_slots][8]: cycles of the run's optimiser lane 0: [0] optimiser turns
                             // ([1] taking in the totals, [2] the BFGS step, [4] publishing the request),
@@ -628,7 +650,8 @@ __device__ __forceinline__ void publish_request(const FitArgs& a, int cs, int la
 template <typename T, int K>
 __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, FitState& S, double* ws,
                                           const double* cred, SeatBook& book, volatile int* s_qcur, uint64_t* part_bar,
-                                          uint32_t ctrl_addr, uint32_t req_bar_addr, const SeatBook* books, int* s_open) {
+                                          uint32_t ctrl_addr, uint32_t req_bar_addr, const SeatBook* books, int* s_open,
+                                          int* s_running) {
   constexpr int W = fit_lanes<K>();
   const bool timing = a.phase_cycles != nullptr && lane == 0;
   long long ta = timing ? clock64() : 0;
@@ -689,6 +712,8 @@ __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, Fi
         }
         if (__shfl_sync(0xffffffffu, hold, 0)) break;
       }
+      Handover* const ho = a.handover;
+      if (ho != nullptr && lane == 0) atomicAdd(&ho->live, 1);  // counted BEFORE the pull: `live` never under-counts
       for (;;) {
         // ONE read per trip: another seat's warp may advance s_qcur at any time, and a second read
         // could return n_queues -- the counter of a group this launch must not touch (its run would
@@ -703,7 +728,68 @@ __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, Fi
         __syncwarp();
         r = -1;
       }
-      if (r < 0) break;
+      if (r < 0) {
+        // the launch's queues are drained
+        if (ho == nullptr) break;
+        int ticket = -1;
+        if (lane == 0) {
+          atomicSub(&ho->live, 1);
+          // the last seat of the cluster to run dry waits for a run of a cluster that carries several
+          if (*(volatile int*)s_running == 0) ticket = atomicAdd(&ho->requests, 1);
+        }
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket < 0 || ticket >= kHandoverSlots) break;
+        double* hs = ho->slots + (size_t)ticket * a.handover_slot_d;
+        // Waits at most kHandoverWaitNs: a cluster with several runs answers at the next turn of one of
+        // its seats, and no cluster gains runs once the queues are drained -- when nobody answers
+        // within a few turns nobody will.  Leaving is a CAS on the slot's flag (0 -> 2); an answer is the
+        // other CAS (0 -> 1): exactly one of them wins, so a run is never handed to a cluster that left.
+        int got = 0;  // 1: a run arrived, 2: nothing to take over
+        const unsigned long long t_wait0 = global_ns();
+        while (got == 0) {
+          if (lane == 0) {
+            int flag;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(flag) : "l"(hs) : "memory");
+            if (flag == 1) {
+              got = 1;
+            } else {
+              int live;
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(live) : "l"(&ho->live) : "memory");
+              if (live == 0 || global_ns() - t_wait0 > kHandoverWaitNs) {
+                got = atomicCAS(reinterpret_cast<int*>(hs), 0, 2) == 0 ? 2 : 1;
+                if (got == 1) __threadfence();
+              } else {
+                __nanosleep(400);
+              }
+            }
+          }
+          got = __shfl_sync(0xffffffffu, got, 0);
+        }
+        if (got == 2) break;
+        // take the run over: FitState and workspace from the slot, the workspace pointer re-aimed
+        {
+          const int* hi = reinterpret_cast<const int*>(hs);
+          const int h_slot = hi[1], h_prog = hi[2], h_k = hi[3];
+          double* dst = reinterpret_cast<double*>(&S);
+          for (int i = lane; i < kFitStateDoubles; i += 32) dst[i] = hs[kHandoverHead + i];
+          const int nws = fit_workspace_doubles(h_k);
+          for (int i = lane; i < nws; i += 32) ws[i] = hs[kHandoverHead + kFitStateDoubles + i];
+          __syncwarp();
+          if (lane == 0) {
+            S.ws = ws;
+            book.slot = h_slot;
+            book.t0 = *reinterpret_cast<const unsigned long long*>(hs + 2);
+            book.n_pass = *reinterpret_cast<const long long*>(hs + 3);
+            if (timing) book.t_seated = clock64(), book.t_logic = 0, book.t_take = book.t_step = book.t_pub = 0, book.ns_seated = (long long)global_ns();
+            atomicAdd(s_running, 1);
+          }
+          __syncwarp();
+          my_prog = h_prog;
+          my_k = h_k;
+          fresh = true;  // the program goes round with the request
+        }
+        break;  // the run was about to publish its request: do that
+      }
       const int prog = a.run_prog[r];
       const int slot = a.run_slot[r];
       const int k = a.pt.k[prog];
@@ -715,6 +801,7 @@ __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, Fi
           info[2] = 0;
           info[3] = 0;
           a.out_loss[slot] = 0.0;
+          if (ho != nullptr) atomicSub(&ho->live, 1);
         }
         continue;
       }
@@ -723,6 +810,7 @@ __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, Fi
       fresh = true;
       fit_init<W>(S, k, ws, a.x0 + (int64_t)slot * a.kstride);
       if (lane == 0) {
+        atomicAdd(s_running, 1);
         book.slot = slot;
         book.t0 = 0ull;
         book.n_pass = 0;
@@ -734,9 +822,55 @@ __device__ __forceinline__ bool seat_turn(const FitArgs& a, int lane, int cs, Fi
     const int act = fit_step_call<W>(S, a.O);
     __syncwarp();  // the state written back by the step is visible to every lane
     if (timing) book.t_step += clock64() - tb;
-    if (act == VSR_NEED_EVAL) break;
+    if (act == VSR_NEED_EVAL) {
+      // a cluster that carries several runs answers the ticket of a waiting one with THIS run
+      Handover* const ho = a.handover;
+      if (ho == nullptr) break;
+      int o = -1;
+      if (lane == 0 && *(volatile int*)s_running >= 2) {
+        int req, off;
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(req) : "l"(&ho->requests) : "memory");
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(off) : "l"(&ho->offers) : "memory");
+        while (off < req && off < kHandoverSlots) {
+          const int old = atomicCAS(&ho->offers, off, off + 1);
+          if (old == off) {
+            o = off;
+            break;
+          }
+          off = old;
+        }
+      }
+      o = __shfl_sync(0xffffffffu, o, 0);
+      if (o < 0) break;
+      double* hs = ho->slots + (size_t)o * a.handover_slot_d;
+      const double* src = reinterpret_cast<const double*>(&S);
+      for (int i = lane; i < kFitStateDoubles; i += 32) hs[kHandoverHead + i] = src[i];
+      const int nws = fit_workspace_doubles(my_k);
+      for (int i = lane; i < nws; i += 32) hs[kHandoverHead + kFitStateDoubles + i] = ws[i];
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        int* hi = reinterpret_cast<int*>(hs);
+        hi[1] = book.slot;
+        hi[2] = my_prog;
+        hi[3] = my_k;
+        *reinterpret_cast<unsigned long long*>(hs + 2) = book.t0;
+        *reinterpret_cast<long long*>(hs + 3) = book.n_pass;
+        __threadfence();
+        // the waiting cluster may have given up (flag 2): then the run stays here
+        o = atomicCAS(reinterpret_cast<int*>(hs), 0, 1) == 0 ? o : -1;
+        if (o >= 0) atomicSub(s_running, 1);
+      }
+      o = __shfl_sync(0xffffffffu, o, 0);
+      if (o < 0) break;
+      my_prog = -1;  // the run lives on elsewhere (it stays counted in `live`)
+      fresh = false;
+      continue;
+    }
     // finished: results out, seat free, try to seat another run in this same turn
     if (lane == 0) {
+      if (a.handover != nullptr) atomicSub(&a.handover->live, 1);
+      atomicSub(s_running, 1);
       const int slot = book.slot;
       double* oc = a.out_consts + (int64_t)slot * a.kstride;
       double* ol = a.out_lastx + (int64_t)slot * a.kstride;
@@ -797,6 +931,7 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
   __shared__ int s_ticket[kMaxSeats];                      // sweeper warps of this CTA that finished seat g's requests
   __shared__ int s_qcur;  // first queue of this launch that is not drained yet
   __shared__ int s_open;  // seats of this cluster that still take runs (leader CTA)
+  __shared__ int s_running;  // seats of this cluster that hold a run (leader CTA)
 
   const int cs = (int)cluster.num_blocks();
   const int crank = (int)cluster.block_rank();
@@ -837,6 +972,7 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
     mbar_fence_init();
     s_qcur = 0;
     s_open = a.seats;
+    s_running = 0;
   }
   if (tid < kMaxSeats) {
     s_book[tid].prog = -1;
@@ -916,7 +1052,8 @@ __global__ void __launch_bounds__((fit_max_threads<T, K>()), (fit_min_ctas<T, K>
         double* seat = VSR_SEAT_STATE(g);
         const bool open = seat_turn<T, K>(a, lane, cs, *reinterpret_cast<FitState*>(seat), seat + kFitStateDoubles,
                                           seat + a.off_cred, s_book[g], &s_qcur, &s_part_bar[g],
-                                          ctrl0 + 8u * (uint32_t)(g * seat_d), smem_u32(&s_req_bar[g]), s_book, &s_open);
+                                          ctrl0 + 8u * (uint32_t)(g * seat_d), smem_u32(&s_req_bar[g]), s_book, &s_open,
+                                          &s_running);
         if (open)
           opt_wait |= 1u << g;
         else
