@@ -526,6 +526,7 @@ int vsr_create(int device, vsr_handle** out) {
   if (e == cudaSuccess) e = h->d_lists.reserve(256 << 10);
   if (e == cudaSuccess) e = h->d_queue.reserve(64 * sizeof(int32_t));
   if (e == cudaSuccess) e = h->d_partial.reserve(1 << 20);
+  if (e == cudaSuccess) e = h->d_handover.reserve(2 << 20);
   {
     StreamPool& sp = pool_of(device);
     std::lock_guard<std::mutex> lock(sp.mu);

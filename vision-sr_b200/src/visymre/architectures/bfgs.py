@@ -520,6 +520,8 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
         if not (comp.staged and world == 1 and n_cand >= 24 and _opt(cfg, "pipeline", True)):
             yield list(range(n_cand))
             return
+        for j in (1, 2, 3):                    # the side engines exist before the first stage is launched
+            fitter.get_side_engine(eng, j)     # (created once per process: a driver's first call pays)
         remaining = set(range(n_cand))
         n_first = max(8, min((n_cand + 2) // 3, hostpool._POOL_N or n_cand))
         stage_no, t_last = 0, _time.perf_counter()
