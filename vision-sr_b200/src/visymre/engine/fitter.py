@@ -310,6 +310,12 @@ def get_side_engine(main, i):
     key = (id(main), i)
     if key not in _SIDE:
         _SIDE[key] = Engine(main.device)
+        # first use of a stream costs: torch's allocator keeps a pool of blocks per stream and fills it
+        # with cudaMalloc calls (which wait for the device).  Touch both pools of the side stream now.
+        with torch.cuda.stream(side_stream(main.device, i)):
+            for n in (1 << 10, 4 << 20):
+                torch.empty(n, dtype=torch.uint8, device=main.device).zero_()
+        torch.cuda.current_stream(main.device).wait_stream(side_stream(main.device, i))
     return _SIDE[key]
 
 
