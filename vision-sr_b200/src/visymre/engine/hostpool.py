@@ -69,6 +69,17 @@ def warm(n=None):
     pool = get_pool(n)
     if pool is not None:
         list(pool.map(_noop, range(2 * n)))
+    # ... and this process prints one winner per call: sympy imports printers and evaluation rules of a
+    # function class the first time it meets one (tens of ms each)
+    try:
+        import sympy as sp
+        from ..architectures import bfgs as vb
+        from .compiler import parse_skeleton
+        expr = parse_skeleton("((c0)+((c1)*(sin((c2)*(x_1)))))+((cos(x_2))*(tan((c3)+(x_3))))+((exp((c4)*(x_1)))/(ln(Abs((c5)+(x_2)))))"
+                              "+((sqrt(Abs(x_1)))*(asin((c6)/((10)+(Abs(x_1))))))+(((x_1)**(c7))*((pi)**(2)))")
+        str(vb._substitute(expr, [sp.Symbol(f"c{i}") for i in range(8)], [0.5, -1.25, 3.0, 1e-3, 2.5e4, -7.0, 0.25, 1.5]))
+    except Exception:  # noqa: BLE001 -- warming only
+        pass
     return n
 
 
