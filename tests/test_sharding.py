@@ -155,3 +155,50 @@ def test_more_ranks_than_runs_does_not_hang_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=120, cwd=ROOT)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+WORKER_COMPILE = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {pkg!r})
+    os.environ["VSR_HOST_WORKERS"] = "0"          # compile in-process: the sharing logic is what is tested
+    import numpy as np, torch.distributed as dist
+    from src.visymre.architectures import bfgs as vb
+    from src.visymre.workloads import generator as wg
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    beams, td = wg.feynman_beams(n_points=32, n_cand=20, n_restarts=2, limit=1)
+    toks = list(beams[0].tokens) + [list(beams[0].tokens[3])]            # a duplicate
+    toks.append([td.word2id["S"], td.word2id["add"], td.word2id["x_1"], td.word2id["F"]])   # incomplete: raises
+    cfg = wg.make_cfg(2)
+    variables = list(td.total_variables)
+    comp = vb._Compiling(toks, cfg, td, variables, share=(rank, world))
+    mine = len(comp.mine)
+    out = comp.exchange()
+    vb._COMPILED.clear()
+    alone = vb._Compiling(toks, cfg, td, variables).wait()
+    assert len(out) == len(alone) == len(toks)
+    assert 0 < mine < len(toks)                                           # the work was dealt, not repeated
+    for a, b in zip(out, alone):
+        assert isinstance(a, Exception) == isinstance(b, Exception)
+        if not isinstance(a, Exception):
+            assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2].insns, b[2].insns) and np.array_equal(a[2].imms, b[2].imms)
+    assert isinstance(out[-1], Exception)
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+""")
+
+
+def test_ranks_share_the_skeleton_compilation_gloo(tmp_path):
+    """refine_hypotheses on N ranks: every rank compiles every N-th missing skeleton and one
+    all_gather_object hands the programs (and the per-candidate exceptions) round."""
+    script = tmp_path / "worker_compile.py"
+    script.write_text(WORKER_COMPILE.format(pkg=PKG))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("ok") == 2
