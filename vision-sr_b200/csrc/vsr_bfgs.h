@@ -13,13 +13,13 @@
 //   ScalarFunction caching      scipy/optimize/_differentiable_functions.py:128-420
 //   '2-point' forward difference scipy/optimize/_numdiff.py:580-700
 //
-// Why a state machine: on the GPU one cluster owns one (candidate, restart) run.  WARP 0
-// of the leader CTA advances the optimiser until it needs the objective at a new point,
-// then returns VSR_NEED_EVAL; ALL threads of the cluster then sweep the data points
-// together (they reach the sweep convergently, so warp shuffles and barriers are legal),
-// and warp 0 resumes.  scipy's nested calls (BFGS -> line search -> phi/derphi ->
-// ScalarFunction) are flattened into one protothread-style function; every variable
-// that lives across an evaluation is a member of FitState.
+// Why a state machine: on the GPU the optimiser of a run is ONE warp of its cluster's leader CTA
+// (vsr_kernels.cuh: seat_turn).  It advances the run until the objective is needed at a new point,
+// returns VSR_NEED_EVAL, the request goes out to the sweeping warps of the cluster, and the same
+// warp resumes the run when the totals of the sweep have come back.  scipy's nested calls (BFGS ->
+// line search -> phi/derphi -> ScalarFunction) are flattened into one protothread-style function;
+// every variable that lives across an evaluation is a member of FitState -- which is also what
+// travels when a run is handed over to another cluster.
 //
 // Execution model of fit_step on the device (a single GPU thread is ~30x slower than a
 // CPU core on serial code, so the linear algebra must not be serial): all 32 lanes of the

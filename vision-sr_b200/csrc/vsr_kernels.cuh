@@ -1,21 +1,22 @@
 // vsr_kernels.cuh -- sm_100a kernels of the refinement engine.
 //
 //   fit_kernel<T,K,P>   PERSISTENT thread-block clusters that keep several (candidate, restart)
-//                       runs in flight each ("seats"): reserved warps of the leader CTA advance
-//                       the BFGS state machines (vsr_bfgs.h) of one half of the seats while
-//                       every other warp of the cluster sweeps its slice of the points --
-//                       TMA-staged once into distributed shared memory -- through the
-//                       interpreter (vsr_interp.h) for the other half.  Replaces
-//                       minimize(safe_loss, x0, 'BFGS') + the lambdified loss
-//                       (reference bfgs.py:102-118).
+//                       runs in flight each ("seats").  A pass of a run is a dataflow of messages
+//                       through distributed shared memory: the seat's optimiser warp (leader CTA)
+//                       advances the BFGS state machine (vsr_bfgs.h) and sends the next request;
+//                       every other warp of the cluster sweeps its part of the points -- TMA-staged
+//                       once into shared memory -- through the interpreter (vsr_interp.h) and the
+//                       CTAs' partial sums travel back.  Replaces minimize(safe_loss, x0, 'BFGS') +
+//                       the lambdified loss (reference bfgs.py:102-118).
 //   eval_kernel<T,K,P>  batched loss (+ gradient) of (program, constants) pairs; grid.y
 //                       splits the points.  Replaces bfgs.py:106-112 and :120-132.
+//   eval_tile_kernel    the same over chunks of the points that all pairs of a launch share (N >= 5e5).
 //   eval_finalize       deterministic fixed-order sum of the split partials.
 //
 // Work mapping: lanes stride over points (coalesced column reads), P points per thread
-// share one instruction decode; per-thread partial sums are fp64 and parked in shared memory,
-// one warp per component sums them (block_totals); fixed order throughout, so results are
-// reproducible run to run.
+// share one instruction decode; per-thread partial sums are fp64 and parked in shared memory, then
+// summed over the warp by shuffles (fit_kernel: warp_totals) or per component by one warp
+// (eval kernels: block_totals); fixed order throughout, so results are reproducible run to run.
 #ifndef VSR_KERNELS_CUH_
 #define VSR_KERNELS_CUH_
 

@@ -570,7 +570,6 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
                 start[li * R + r, :k] = v
         return start
 
-    fitted = {}     # candidate -> (lastx rows [R, k], final scores [R])   (one GPU)
     win_of = {}     # candidate -> record of the all-gather                (sharded)
     launched = []
     for si, stage in enumerate(_stages()):
