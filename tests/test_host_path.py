@@ -142,3 +142,30 @@ def test_derivative_is_constant_shortcut_agrees_with_sympy():
                  "(c0)*(tan(cos((x_1)*(x_3)))+((x_2)*(x_4)))/((x_1)+(x_2))"]:
         e = sp.sympify(text)
         assert bool(vbfgs._derivative_is_constant(e, c0)) == bool(sp.diff(e, c0).is_constant()), text
+
+
+def test_a_dead_worker_does_not_fail_the_beam(beams, monkeypatch):
+    """The symbolic work runs in worker processes; when one dies the task is compiled in-process and
+    the next call gets a fresh pool (the reference's pool is created per call, model.py:490)."""
+    import os
+    from src.visymre.engine import hostpool
+    bs, td = beams
+    cfg = wg.make_cfg(3)
+    monkeypatch.setenv("VSR_HOST_WORKERS", "2")
+    toks = list(bs[0].tokens)
+    vbfgs._COMPILED.clear()
+    want = vbfgs._compile_candidates(toks, cfg, td, list(td.total_variables))
+    vbfgs._COMPILED.clear()
+    pool = hostpool.get_pool(2)
+    for pid in list(pool._processes):                 # kill the workers under the pool
+        os.kill(pid, 9)
+    got = vbfgs._compile_candidates(toks, cfg, td, list(td.total_variables))
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert isinstance(a, Exception) == isinstance(b, Exception)
+        if not isinstance(a, Exception):
+            assert a[0] == b[0] and np.array_equal(a[2].insns, b[2].insns)
+    vbfgs._COMPILED.clear()
+    again = vbfgs._compile_candidates(toks, cfg, td, list(td.total_variables))    # a fresh pool serves it
+    assert len(again) == len(want) and hostpool._POOL is not None
+    hostpool.shutdown()

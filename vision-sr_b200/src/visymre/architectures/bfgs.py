@@ -150,10 +150,23 @@ def _prepare_prune_async(prog, small, variables, cfg, many=True):
     """``prepare_prune`` of one candidate: in the host pool when there is one and the caller has
     several candidates to prepare.  Returns a function that waits for the result."""
     pool = hostpool.get_pool(_host_workers(cfg)) if many else None
-    if pool is None:
+    fut = None
+    if pool is not None:
+        try:
+            fut = pool.submit(hostpool.prune_task, (prog, small, list(variables)))
+        except Exception:  # noqa: BLE001 -- broken pool: do it here
+            hostpool.shutdown()
+    if fut is None:
         got = prepare_prune(prog, small, variables)
         return lambda: got
-    return pool.submit(hostpool.prune_task, (prog, small, list(variables))).result
+
+    def wait():
+        try:
+            return fut.result()
+        except Exception:  # noqa: BLE001 -- a worker died: do it here, the next call starts a fresh pool
+            hostpool.shutdown()
+            return prepare_prune(prog, small, variables)
+    return wait
 
 
 def _derivative_is_constant(expr, sym):
@@ -232,6 +245,7 @@ class _Compiling:
     def __init__(self, pred_strs, cfg, test_data, variables, share=None):
         """``share = (rank, world)``: the ranks of a process group were handed the same beam; each
         compiles every world-th missing skeleton and ``exchange()`` hands the programs round."""
+        self._cfg, self._td, self._variables = cfg, test_data, variables
         self.keys = keys = [_cache_key(t, cfg, test_data, variables) for t in pred_strs]
         self.out = out = [_COMPILED.get(k) for k in keys]
         miss = [i for i, h in enumerate(out) if h is None]
@@ -261,7 +275,12 @@ class _Compiling:
             id2word = dict(test_data.id2word)
             for j in range(0, len(todo), per):
                 ch = todo[j:j + per]
-                fut = pool.submit(hostpool.compile_chunk, ([list(keys[i][0]) for i in ch], bits, id2word, list(variables)))
+                try:
+                    fut = pool.submit(hostpool.compile_chunk, ([list(keys[i][0]) for i in ch], bits, id2word, list(variables)))
+                except Exception:  # noqa: BLE001 -- the pool is broken (a worker died earlier): a future that says so
+                    from concurrent.futures import Future
+                    fut = Future()
+                    fut.set_exception(RuntimeError("host pool unavailable"))
                 for i in ch:
                     self.owner[i] = len(self.pending)
                 self.pending.append((fut, ch))
@@ -323,7 +342,17 @@ class _Compiling:
             fut, ch = self.pending[pos]
             if fut is None:
                 continue
-            for i, r in zip(ch, fut.result()):
+            try:
+                got = fut.result()
+            except Exception:  # noqa: BLE001 -- a worker died (BrokenProcessPool ...): compile the task here
+                hostpool.shutdown()               # the next call starts a fresh pool
+                got = []
+                for i in ch:
+                    try:
+                        got.append(compile_tokens(list(self.keys[i][0]), self._cfg, self._td, self._variables))
+                    except Exception as exc:  # noqa: BLE001 -- per candidate (model.py:15-19)
+                        got.append(exc)
+            for i, r in zip(ch, got):
                 self.out[i] = r if isinstance(r, Exception) else _remember(self.keys[i], r)
             self.pending[pos] = (None, ch)
         self._fill_dups()
