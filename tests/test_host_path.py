@@ -169,3 +169,15 @@ def test_a_dead_worker_does_not_fail_the_beam(beams, monkeypatch):
     again = vbfgs._compile_candidates(toks, cfg, td, list(td.total_variables))    # a fresh pool serves it
     assert len(again) == len(want) and hostpool._POOL is not None
     hostpool.shutdown()
+
+
+def test_parse_skeleton_takes_the_direct_path_for_integer_literals(monkeypatch):
+    """Regression: ``Integer`` was only bound when the word occurred in the text, so every skeleton with
+    an integer literal fell through to ``sympify`` (correct, but the slow path)."""
+    import sympy
+    from src.visymre.engine import compiler
+    calls = []
+    real = sympy.sympify
+    monkeypatch.setattr(compiler.sp, "sympify", lambda *a, **k: (calls.append(a), real(*a, **k))[1])
+    e = compiler.parse_skeleton("((c0)+((x_1)**(2)))*((-1)/((c1)+(3)))")
+    assert not calls and sympy.srepr(e) == sympy.srepr(real("((c0)+((x_1)**(2)))*((-1)/((c1)+(3)))"))

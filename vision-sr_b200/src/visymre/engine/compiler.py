@@ -88,7 +88,7 @@ def parse_skeleton(text):
     """``sympy.sympify(text)`` for the skeleton strings of this path (same tree, less overhead)."""
     if not isinstance(text, str) or not _PARSE_SAFE.match(text):
         return sp.sympify(text)
-    ns = {"__builtins__": {}}
+    ns = {"__builtins__": {}, "Integer": sp.Integer}      # (the literals are wrapped below)
     for w in set(_PARSE_WORD.findall(text)):
         if w in _PARSE_NAMES:
             ns[w] = _PARSE_NAMES[w]
