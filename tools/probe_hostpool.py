@@ -16,7 +16,7 @@ t0 = time.perf_counter()
 for t in beams[0].tokens:
     vb.compile_tokens(t, cfg, td, variables)
 print(f"in-process: {(time.perf_counter() - t0) * 1e3 / len(beams[0].tokens):.2f} ms per candidate")
-for n in (4, 8, 12, 15, 16):
+for n in (8, 10, 12, 14, 15):
     os.environ["VSR_HOST_WORKERS"] = str(n)
     hostpool.warm(n)
     ms = []
