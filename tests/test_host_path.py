@@ -181,3 +181,15 @@ def test_parse_skeleton_takes_the_direct_path_for_integer_literals(monkeypatch):
     monkeypatch.setattr(compiler.sp, "sympify", lambda *a, **k: (calls.append(a), real(*a, **k))[1])
     e = compiler.parse_skeleton("((c0)+((x_1)**(2)))*((-1)/((c1)+(3)))")
     assert not calls and sympy.srepr(e) == sympy.srepr(real("((c0)+((x_1)**(2)))*((-1)/((c1)+(3)))"))
+
+
+def test_stage_plan_of_the_staged_fit():
+    """architectures/bfgs.py:stage_goes -- when the next stage of a fit staged behind the compilation
+    is launched (the GPU tests run the staged path itself; this is its decision rule)."""
+    go = vbfgs.stage_goes
+    assert go(64, 64, 0, 0.0, 15) and go(3, 3, 3, 0.0, 15)          # all that is left always goes
+    assert not go(14, 64, 0, 1.0, 15) and go(15, 64, 0, 0.0, 15)     # first stage: enough to fill the GPU
+    assert not go(40, 49, 1, 0.001, 15)                              # later stage: not before the stragglers
+    assert go(40, 49, 1, 0.005, 15) and not go(30, 49, 1, 0.1, 15)   # ... have kept it waiting; and most is there
+    assert not go(7, 9, 2, 1.0, 15)                                  # fewer than eight: wait for the rest
+    assert not go(40, 49, vbfgs.MAX_STAGES - 1, 1.0, 15)             # the last engine takes everything or nothing

@@ -237,6 +237,24 @@ def _host_workers(cfg):
     return hostpool.default_workers() if n is None else int(n)
 
 
+MAX_STAGES = 4     # the main engine and three side engines
+
+
+def stage_goes(n_ready, n_remaining, stage_no, since_last_s, n_first):
+    """Whether the next stage of a staged fit is launched now: ``n_ready`` of the ``n_remaining``
+    candidates not yet launched are compiled, ``stage_no`` stages are out, the last one went
+    ``since_last_s`` seconds ago.  Everything that is left always goes; the FIRST stage goes as soon as
+    ``n_first`` candidates (enough to fill the GPU) are there; a later one when most of the rest is
+    there and the stragglers have kept it waiting; the last engine only takes all that is left."""
+    if n_ready == n_remaining:
+        return True
+    if stage_no >= MAX_STAGES - 1:
+        return False
+    if stage_no == 0:
+        return n_ready >= n_first
+    return n_ready >= max(8, (3 * n_remaining) // 4) and since_last_s > 4e-3
+
+
 class _Compiling:
     """Skeleton compilation of a beam under way: cache hits are there at once, the misses are tasks in
     the host pool (heaviest skeletons first).  ``wait(indices)`` blocks until those candidates are
@@ -557,14 +575,7 @@ def _bfgs_batch(pred_strs, X, y, cfg, test_data, x0=None, engine=None, lazy_stri
         while remaining:
             ready = comp.ready(remaining)
             now = _time.perf_counter()
-            go = len(ready) == len(remaining)
-            if not go and stage_no == 0:
-                go = len(ready) >= n_first
-            elif not go and stage_no < 3:
-                # a later stage goes when most of the rest is there and the stragglers keep it waiting
-                go = len(ready) >= max(8, (3 * len(remaining)) // 4) and now - t_last > 4e-3
-            if go and stage_no == 3:
-                go = len(ready) == len(remaining)      # the last engine takes all that is left
+            go = stage_goes(len(ready), len(remaining), stage_no, now - t_last, n_first)
             if not go:
                 _time.sleep(2e-4)
                 continue
